@@ -160,6 +160,18 @@ int tgsf_collect(tgsf_ctx *ctx, tgsf_read_result *reads, uint32_t n_reads, tgsf_
  * kernels only, and H2D+kernels+D2H. */
 int tgsf_last_timing(tgsf_ctx *ctx, float *kernel_ms, float *total_ms);
 
+/* Device time (ms) of each pipeline stage of the batch retired by the last collect, measured with
+ * CUDA events on the slot's stream (bench.py's per-kernel roofline comes from here). */
+#define TGSF_N_STAGES 7
+#define TGSF_STAGE_RAW_SCAN 0    /* K1 over the reads (tile table + k_scan_tiles) */
+#define TGSF_STAGE_RAW_FINAL 1   /* quality band, histogram, raw 5'/3' tables */
+#define TGSF_STAGE_MID_SCAN 2    /* K3 k_mid_scan, all adapters (chunk table included) */
+#define TGSF_STAGE_RESOLVE 3     /* K3 k_mid_count + k_ends (start search, traceback, thresholds) */
+#define TGSF_STAGE_REGIONS 4     /* K3 k_mid_emit + K5 regions / piece compaction */
+#define TGSF_STAGE_KMER 5        /* K4 */
+#define TGSF_STAGE_CLEAN 6       /* K1 over the kept pieces + clean decisions + clean 5'/3' */
+int tgsf_last_stage_ms(tgsf_ctx *ctx, float *out, int n);
+
 /* Replaces: the per-thread accumulators of TGSFilterTask and their merge (T.cpp:1796-1806,
  * 3208-3213).  Cumulative since create / the last reset.  All batches must have been collected. */
 int tgsf_counter_layout_get(const tgsf_ctx *ctx, tgsf_counter_layout *out);

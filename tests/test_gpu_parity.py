@@ -1,0 +1,292 @@
+"""GPU parity suite (runs on the B200 box): libtgsf_cuda through its C-ABI against the CPU oracle
+on the same seeded inputs, and against the committed golden fixtures of the reference.
+Everything is integer / byte work, so every comparison is bit-exact (np.array_equal on the raw
+structs); the only floating-point step is the fp64 mean-quality division, which is evaluated
+exactly as the reference writes it (double(sumQ) / len) and is therefore also compared exactly
+through the keep/drop decisions and histogram bins."""
+import numpy as np
+import pytest
+
+import golden_lib
+import oracle_lib
+from tgsfilter_b200 import _capi, records, synth
+from tgsfilter_b200.engine import FilterEngine, align_hw
+from tgsfilter_b200.params import ADAPTER_LIB, FilterParams, rev_comp
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(params, batch, n_batches=1):
+    """Engine vs oracle: per-read results, pieces, all counters."""
+    o_reads, o_pieces, o_cnt = oracle_lib.run(params, batch)
+    with FilterEngine(params) as eng:
+        if n_batches == 1:
+            reads, pieces = eng.run(batch)
+        else:
+            # several batches in flight; results concatenated with re-based piece indices
+            bounds = np.linspace(0, batch.n_reads, n_batches + 1).astype(int)
+            parts = [batch.slice(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:])]
+            outs = []
+            i = 0
+            for part in parts:
+                if len(eng._inflight) == 2:
+                    outs.append(eng.collect())
+                eng.submit(part)
+                i += 1
+            while eng._inflight:
+                outs.append(eng.collect())
+            reads = np.concatenate([o[0] for o in outs])
+            pieces = np.concatenate([o[1] for o in outs])
+            pb, rb = 0, 0
+            k = 0
+            for (r, p), part in zip(outs, parts):
+                reads["piece_begin"][rb:rb + len(r)] += pb
+                pieces["read"][k:k + len(p)] += rb
+                pb += len(p)
+                k += len(p)
+                rb += len(r)
+        cnt = eng.counters().flat
+        assert eng.launch_count() > 0
+    for f in reads.dtype.names:
+        np.testing.assert_array_equal(reads[f], o_reads[f], err_msg=f"reads.{f}")
+    assert len(pieces) == len(o_pieces)
+    for f in pieces.dtype.names:
+        np.testing.assert_array_equal(pieces[f], o_pieces[f], err_msg=f"pieces.{f}")
+    bad = np.nonzero(cnt != o_cnt)[0]
+    assert bad.size == 0, f"counter words differ at {bad[:10]} gpu={cnt[bad[:10]]} oracle={o_cnt[bad[:10]]}"
+    return reads, pieces, cnt
+
+
+def test_library_identifies_sm100a():
+    assert b"sm_100a" in _capi.load().tgsf_version()
+
+
+def test_align_golden_edlib_vectors():
+    cases = golden_lib.load_edlib()
+    out = align_hw([(q, t, k) for q, t, k, *_ in cases])
+    for (q, t, k, d, alen, locs), r in zip(cases, out):
+        assert int(r["edit_distance"]) == d, (q, t, k)
+        assert int(r["n_locations"]) == len(locs), (q, t, k)
+        assert int(r["align_len"]) == alen, (q, t, k)
+        if locs:
+            assert (int(r["first_start"]), int(r["first_end"])) == locs[0]
+            assert (int(r["last_start"]), int(r["last_end"])) == locs[-1]
+
+
+def test_align_random_vs_oracle_all_word_counts():
+    rng = np.random.default_rng(11)
+    a = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs = []
+    for i in range(3000):
+        ql = int(rng.integers(1, 257))
+        alpha = a if i % 4 else a[:2]
+        q = alpha[rng.integers(0, len(alpha), ql)].tobytes()
+        mode = i % 3
+        if mode == 0:
+            t = alpha[rng.integers(0, len(alpha), int(rng.integers(1, 500)))].tobytes()
+        elif mode == 1:
+            t = (alpha[rng.integers(0, len(alpha), int(rng.integers(0, 90)))].tobytes()
+                 + synth.mutate(q, float(rng.random() * 0.3), rng)
+                 + alpha[rng.integers(0, len(alpha), int(rng.integers(0, 90)))].tobytes()) or b"A"
+        else:
+            t = (q[:max(1, ql // 4)] * 9)[:int(rng.integers(1, 400))]
+        k = [-1, ql, ql + 3, max(0, ql - 3), int(ql * 0.1) + 1, int(rng.integers(0, ql + 1))][i % 6]
+        pairs.append((q, t, k))
+    out = align_hw(pairs)
+    for p, r in zip(pairs, out):
+        o, _ = oracle_lib.align_hw(*p)
+        for f in ("edit_distance", "n_locations", "align_len", "first_start", "first_end",
+                  "last_start", "last_end", "loc_hash"):
+            assert int(r[f]) == (o[f] & 0xffffffff if f == "loc_hash" else o[f]), (f, p)
+
+
+@pytest.mark.parametrize("name", golden_lib.perread_names())
+def test_golden_reference_fixtures(name):
+    params, batch, exp = golden_lib.load_perread(name)
+    with FilterEngine(params) as eng:
+        reads, pieces = eng.run(batch)
+        cnt = eng.counters().flat
+        layout = eng.layout
+    recs = records.format_records(batch, pieces, fastq=exp["outfq"] == 1)
+    golden_lib.check_against_golden(exp, layout, cnt, recs)
+
+
+@pytest.mark.parametrize("cfg,n", [(1, 400), (2, 300), (3, 60), (4, 600), (5, 300)])
+def test_configs_vs_oracle(cfg, n):
+    batch = synth.make_config(cfg, n, max_len=250000)
+    params = synth.config_params(cfg)
+    if cfg == 5:
+        params.min_repeat = 40
+    _compare(params, batch)
+
+
+def test_config3_discard_and_split():
+    batch = synth.make_config(3, 80, max_len=200000)
+    params = synth.config_params(3)
+    r1, p1, _ = _compare(params, batch)
+    assert (r1["n_pieces"] > 1).any(), "the fixture should contain at least one split read"
+    params.discard = True
+    _compare(params, batch)
+
+
+def test_config4_trims_and_band():
+    batch = synth.make_config(4, 500)
+    params = synth.config_params(4)
+    params.head_trim, params.tail_trim = 12, 9
+    _compare(params, batch)
+
+
+def test_multiple_batches_in_flight_accumulate():
+    batch = synth.make_config(1, 300)
+    params = synth.config_params(1)
+    params.head_trim = 4
+    _compare(params, batch, n_batches=5)
+
+
+def test_ultra_long_read_uses_global_bins():
+    # one 350 kb read: bins beyond SCAN_SMEM_BINS (102 kb) take the L2-atomic path
+    rng = np.random.default_rng(3)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs, quals = [], []
+    for L in (350_123, 99, 100, 101, 3199, 3200, 3201, 6400, 1, 4, 5, 150, 299, 300, 301):
+        seqs.append(acgt[rng.integers(0, 4, L)].tobytes())
+        quals.append((rng.integers(5, 40, L).astype(np.uint8) + 33).tobytes())
+    ad = ADAPTER_LIB[8]
+    s0 = bytearray(seqs[0])
+    for pos in (50_000, 200_000, 349_000):
+        s0[pos:pos + len(ad)] = ad
+    seqs[0] = bytes(s0)
+    batch = synth.pack_reads(seqs, quals)
+    params = FilterParams(min_len=100, min_q=5.0, head_trim=0, tail_trim=0,
+                          adapters=[ad, rev_comp(ad)]).apply_read_type("ont")
+    reads, pieces, _ = _compare(params, batch)
+    assert int(reads["n_mid"][0]) >= 3
+
+
+def test_edge_cases_empty_short_weird_bytes():
+    seqs = [b"", b"A", b"ACG", b"ACGTA", b"acgtnNRYacgt" * 30, b"N" * 200, ADAPTER_LIB[0],
+            ADAPTER_LIB[0] * 8, b"ACGT" * 100, bytes(range(33, 127)) * 3]
+    quals = [bytes([40] * len(s)) for s in seqs]
+    quals[4] = bytes([33 + (i % 60) for i in range(len(seqs[4]))])
+    quals[9] = bytes([127 - (i % 90) for i in range(len(seqs[9]))])
+    batch = synth.pack_reads(seqs, quals)
+    params = FilterParams(min_len=100, min_q=0.0, head_trim=2, tail_trim=2,
+                          adapters=[ADAPTER_LIB[0], ADAPTER_LIB[1]]).apply_read_type("hifi")
+    reads, _, _ = _compare(params, batch)
+    assert int(reads["status"][0]) == _capi.READ_EMPTY
+    # an entirely empty batch is legal
+    with FilterEngine(params) as eng:
+        r, p = eng.run(synth.pack_reads([], []))
+        assert len(r) == 0 and len(p) == 0
+
+
+def test_fasta_input_without_qualities():
+    batch = synth.make_config(1, 150, max_len=20000)
+    batch = synth.ReadBatch(batch.bases, None, batch.offsets, batch.names)
+    lower = batch.bases.copy()
+    lower[::7] |= 0x20  # sprinkle lower case: exercises the 'g' / 't' typos of the FASTA path
+    batch.bases = lower
+    params = synth.config_params(1)
+    params.qtype = 0
+    params.head_trim = 3
+    _compare(params, batch)
+
+
+def test_qc_only_mode():
+    batch = synth.make_config(2, 200, max_len=60000)
+    params = FilterParams(filter=False, only_qc=True, adapters=[])
+    _, pieces, _ = _compare(params, batch)
+    assert (pieces["status"] == _capi.PIECE_QC_ONLY).all()
+
+
+def test_region_pool_overflow_is_retried():
+    # -M 10 / -S 0.8 on low-complexity reads: every read has hundreds of equal-score middle
+    # locations, far beyond the initial pool; collect() must grow the pool and re-run the tail.
+    rng = np.random.default_rng(8)
+    ad = b"ACACACACACACACACACACAC"
+    seqs, quals = [], []
+    for i in range(600):
+        L = int(rng.integers(2000, 4000))
+        seqs.append((b"AC" * (L // 2 + 1))[:L])
+        quals.append(bytes([50] * L))
+    batch = synth.pack_reads(seqs, quals)
+    params = FilterParams(min_len=100, min_q=1.0, head_trim=0, tail_trim=0, mid_match_len=10,
+                          extra_len=0, adapters=[ad]).apply_read_type("ont")
+    reads, _, _ = _compare(params, batch)
+    assert int(reads["n_mid"].sum()) > 65536
+
+
+def test_submit_device_resident_inputs():
+    import torch
+    batch = synth.make_config(1, 200)
+    params = synth.config_params(1)
+    o_reads, o_pieces, o_cnt = oracle_lib.run(params, batch)
+    d_b = torch.from_numpy(batch.bases).cuda()
+    d_q = torch.from_numpy(batch.quals).cuda()
+    d_o = torch.from_numpy(batch.offsets.astype(np.int64)).cuda()
+    torch.cuda.synchronize()
+    with FilterEngine(params) as eng:
+        eng.submit_device(d_b.data_ptr(), d_q.data_ptr(), d_o.data_ptr(), batch.n_reads,
+                          batch.n_bases, keep=(d_b, d_q, d_o))
+        reads, pieces = eng.collect()
+        cnt = eng.counters().flat
+        k_ms, t_ms = eng.last_timing()
+    assert np.array_equal(reads, o_reads) and np.array_equal(pieces, o_pieces)
+    assert np.array_equal(cnt, o_cnt)
+    assert k_ms > 0 and t_ms >= k_ms
+
+
+def test_prepass_counts_and_library_search_vs_oracle():
+    from tgsfilter_b200 import prepass
+    z = np.load(golden_lib.HERE + "/prepass.npz")
+    e5, e3 = z["ends5p"], z["ends3p"]
+    c5, c3, m5, m3 = prepass.device_prepass(e5, e3, ADAPTER_LIB, 0.9)
+    np.testing.assert_array_equal(c5, oracle_lib.base_content_counts(e5))
+    np.testing.assert_array_equal(c3, oracle_lib.base_content_counts(e3))
+    np.testing.assert_array_equal(m5, oracle_lib.adapter_search(e5, ADAPTER_LIB, 0.9))
+    np.testing.assert_array_equal(m3, oracle_lib.adapter_search(e3, ADAPTER_LIB, 0.9))
+    # and the reference's own decisions on the same ends (golden fixture)
+    res = prepass.resolve(c5, c3, m5, m3, n=e5.shape[0], end_bias=1.0, mid_sim=0.9, bc_len=150,
+                          read_type="ont", lib=ADAPTER_LIB)
+    assert (res.trim5p, res.trim3p) == (int(z["trim5p"]), int(z["trim3p"]))
+    assert res.adapter5p == z["adapter5p"].tobytes()
+    assert np.float32(res.dep5p) == np.float32(z["dep5p"])
+
+
+def test_full_size_properties_config1():
+    """BASELINE config 1 at full size (20 000 reads, ~0.3 Gbases): size-independent properties."""
+    batch = synth.make_config(1, 20000, with_names=False)
+    params = synth.config_params(1)
+    with FilterEngine(params) as eng:
+        reads, pieces = eng.run(batch)
+        c = eng.counters()
+    lens = np.diff(batch.offsets.astype(np.int64))
+    # every base is counted exactly once in the raw bins and the raw histogram
+    assert int(c.raw_bin_cnt[:, 4].sum()) == batch.n_bases
+    assert int(c.raw_hist.sum()) == batch.n_bases
+    # conservation: input = lowQ + trimmed + short + lowQ-after-split + emitted
+    emitted = int(pieces["len"][pieces["status"] == _capi.PIECE_EMIT].sum())
+    d = c.drop_info
+    assert batch.n_bases == int(d[1]) + int(d[10]) + int(d[12]) + int(d[14]) + int(d[16]) + emitted
+    assert int(c.clean_hist.sum()) == emitted
+    # adapter classes partition the evaluated reads
+    assert int(d[2:10].sum()) == int((reads["status"] == _capi.READ_EVALUATED).sum())
+    # sum_q is the per-read quality sum
+    k = 1234
+    s, e = int(batch.offsets[k]), int(batch.offsets[k + 1])
+    assert int(reads["sum_q"][k]) == int(batch.quals[s:e].astype(np.int64).sum() - 33 * (e - s))
+    # pieces are sorted, inside their read, and non-overlapping
+    assert (np.diff(pieces["read"]) >= 0).all()
+    assert ((pieces["start"] >= 0) & (pieces["start"] + pieces["len"] <= lens[pieces["read"]])).all()
+    # idempotence: filtering the emitted pieces again changes nothing
+    em = pieces[pieces["status"] == _capi.PIECE_EMIT][:2000]
+    seqs, quals = [], []
+    for p in em:
+        b, q = batch.read(int(p["read"]))
+        seqs.append(b[p["start"]:p["start"] + p["len"]].tobytes())
+        quals.append(q[p["start"]:p["start"] + p["len"]].tobytes())
+    again = synth.pack_reads(seqs, quals)
+    with FilterEngine(params) as eng:
+        r2, p2 = eng.run(again)
+    assert (r2["status"] == _capi.READ_EVALUATED).all()
+    assert len(p2) == len(em) and (p2["start"] == 0).all() and (p2["len"] == em["len"]).all()

@@ -26,6 +26,8 @@ FLAG_DISCARD_MID = 4
 READ_EVALUATED, READ_LOWQ, READ_EMPTY = 0, 1, 2
 PIECE_EMIT, PIECE_SHORT_REPEAT, PIECE_LOWQ, PIECE_QC_ONLY = 0, 1, 2, 3
 
+N_STAGES = 7
+STAGE_NAMES = ("raw_scan", "raw_final", "mid_scan", "resolve", "regions", "kmer", "clean")
 DROPINFO_N = 17
 QUAL_HIST_N = 256
 
@@ -109,7 +111,7 @@ ALIGN_RESULT_DTYPE = [("edit_distance", "<i4"), ("n_locations", "<i4"), ("align_
 # every symbol include/tgsf.h declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
     "tgsf_version", "tgsf_last_error", "tgsf_create", "tgsf_destroy", "tgsf_host_alloc",
-    "tgsf_host_free", "tgsf_submit", "tgsf_submit_device", "tgsf_collect", "tgsf_last_timing",
+    "tgsf_host_free", "tgsf_submit", "tgsf_submit_device", "tgsf_collect", "tgsf_last_timing", "tgsf_last_stage_ms",
     "tgsf_counter_layout_get", "tgsf_counters", "tgsf_counters_reset", "tgsf_counters_device",
     "tgsf_launch_count", "tgsf_prepass", "tgsf_align_hw",
 )
@@ -140,6 +142,7 @@ def load() -> C.CDLL:
     lib.tgsf_submit_device.argtypes = [vp, u8p, u8p, u64p, C.c_uint32, C.c_uint64]
     lib.tgsf_collect.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.tgsf_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.tgsf_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.tgsf_counter_layout_get.argtypes = [vp, C.POINTER(CounterLayout)]
     lib.tgsf_counters.argtypes = [vp, u64p, C.c_uint32]
     lib.tgsf_counters_reset.argtypes = [vp]

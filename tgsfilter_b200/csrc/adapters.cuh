@@ -1,0 +1,271 @@
+// K3: adapter search kernels.  Replaces GetEditDistance (T.cpp:1218-1322) = three edlibAlign
+// (HW, PATH) calls per (read, adapter): middle window, 5' window, 3' window.
+//
+//   k_mid_scan    one thread per (1024-column absolute chunk of a read's middle window, adapter):
+//                 HW scan with a q+k-1 column halo, chunk minimum + atomicMin per (read, adapter).
+//                 This is the kernel that dominates the pipeline (INT-ALU bound).
+//   k_mid_count   one thread per (read, adapter) whose best distance is <= k: enumerates the end
+//                 columns (only chunks whose minimum equals the best), runs edlib's PATH step on
+//                 the first location (start search + traceback -> mlen) and the two thresholds.
+//   k_mid_emit    same walk, writes one region per location into the pool.
+//   k_ends        one thread per (read, adapter, end): whole window in one thread.
+#pragma once
+#include "common.cuh"
+#include "myers.cuh"
+
+#define MID_THREADS 128
+#define RES_THREADS 128
+
+struct AdapterCtx {
+    const DevAdapter *ad; // [n_adapters]
+    const u64 *peq_pool;
+};
+
+static __device__ __forceinline__ AdapterTables adapter_tables(const AdapterCtx &C, int a) {
+    const DevAdapter A = C.ad[a];
+    AdapterTables T;
+    T.hw = C.peq_pool + A.peq_off;
+    T.fw = T.hw + 256 * A.nw;
+    T.rv = T.fw + 256 * A.nw;
+    T.qlen = A.qlen;
+    return T;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_mid_scan
+// ---------------------------------------------------------------------------------------------
+// chunk_min: [n_adapters][chunk_stride] u8 (255 = nothing <= 254 / window too short)
+// best_mid:  [n_reads][n_adapters] u32, pre-set to 0xffffffff
+template <int NW>
+__global__ void __launch_bounds__(MID_THREADS)
+k_mid_scan_dyn(DevBatch B, AdapterCtx C, int a, int end_len, const ChunkEntry *__restrict__ chunks,
+               const u32 *__restrict__ n_chunks_ptr, u32 chunk_stride,
+               uint8_t *__restrict__ chunk_min, u32 *__restrict__ best_mid, int n_adapters) {
+    const u32 n_chunks = *n_chunks_ptr; // device-side total (chunk_off[n_reads])
+    extern __shared__ u64 s_peq[]; // [256][NW] top-padded table of adapter a
+    const DevAdapter A = C.ad[a];
+    {
+        const u64 *src = C.peq_pool + A.peq_off;
+        for (int i = threadIdx.x; i < 256 * NW; i += MID_THREADS) s_peq[i] = src[i];
+    }
+    __syncthreads();
+    const int q = A.qlen;
+    const int k = A.k_mid;
+    const uint4 *__restrict__ b16 = (const uint4 *)B.bases;
+
+    for (u32 ci = blockIdx.x * MID_THREADS + threadIdx.x; ci < n_chunks;
+         ci += gridDim.x * MID_THREADS) {
+        const ChunkEntry ce = chunks[ci];
+        const u64 rs = B.offsets[ce.read];
+        const u64 re = B.offsets[ce.read + 1];
+        const i64 len = (i64)(re - rs);
+        uint8_t result = 255;
+        if (k > 0 && len - 2 * (i64)end_len >= (i64)q) { // tsmLen >= qLen, T.cpp:1237
+            const u64 mb = rs + (u64)end_len, me = re - (u64)end_len; // middle window
+            const u64 cb = (u64)ce.chunk * MID_CHUNK;
+            const u64 ob = max(cb, mb), oe = min(cb + MID_CHUNK, me);  // columns this chunk reports
+            u64 sb = ob > (u64)A.halo_mid ? ob - (u64)A.halo_mid : 0;  // restart point
+            if (sb < mb) sb = mb;
+            Myers<NW> s;
+            myers_init_hw<NW>(s, q);
+            int best = 0x7fffffff;
+            // [sb, ob): halo, state only.  [ob, oe): tracked.
+            u64 p = sb;
+            // head: bytes up to the next 16-byte boundary (only the first chunk of a window)
+            while (p < oe && (p & 15ull)) {
+                myers_step<NW, 0, true>(s, s_peq + (u32)B.bases[p] * NW, 0);
+                if (p >= ob) best = min(best, s.score);
+                ++p;
+            }
+            // halo groups (whole 16-byte groups strictly before ob; ob is 16-aligned here)
+            for (; p + 16 <= ob; p += 16) {
+                const uint4 v = __ldg(b16 + (p >> 4));
+                const u32 wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    myers_step<NW, 0, true>(s, s_peq + byte * NW, 0);
+                }
+            }
+            // body groups
+            for (; p + 16 <= oe; p += 16) {
+                const uint4 v = __ldg(b16 + (p >> 4));
+                const u32 wd[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                    myers_step<NW, 0, true>(s, s_peq + byte * NW, 0);
+                    best = min(best, s.score);
+                }
+            }
+            // tail
+            for (; p < oe; ++p) {
+                myers_step<NW, 0, true>(s, s_peq + (u32)B.bases[p] * NW, 0);
+                if (p >= ob) best = min(best, s.score);
+            }
+            if (best <= k) {
+                result = (uint8_t)min(best, 254);
+                atomicMin(best_mid + (u64)ce.read * n_adapters + a, (u32)best);
+            }
+        }
+        chunk_min[(u64)a * chunk_stride + ci] = result;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Enumerate, in ascending order, the end columns of the middle window of read r whose HW score
+// equals d, visiting only the chunks whose minimum is d.  f(p) is called with the absolute byte
+// offset of each such column; return false from f to stop.
+// ---------------------------------------------------------------------------------------------
+template <int NW, typename F>
+static __device__ void mid_for_each_end(const DevBatch &B, const AdapterTables &T,
+                                        const DevAdapter &A, int a, int end_len, u32 r, int d,
+                                        const u32 *__restrict__ chunk_off,
+                                        const ChunkEntry *__restrict__ chunks, u32 n_chunks,
+                                        const uint8_t *__restrict__ chunk_min, F f) {
+    const u64 rs = B.offsets[r], re = B.offsets[r + 1];
+    const u64 mb = rs + (u64)end_len, me = re - (u64)end_len;
+    for (u32 ci = chunk_off[r]; ci < chunk_off[r + 1]; ++ci) {
+        if (chunk_min[(u64)a * n_chunks + ci] != (uint8_t)min(d, 254)) continue;
+        const u64 cb = (u64)chunks[ci].chunk * MID_CHUNK;
+        const u64 ob = max(cb, mb), oe = min(cb + MID_CHUNK, me);
+        u64 sb = ob > (u64)A.halo_mid ? ob - (u64)A.halo_mid : 0;
+        if (sb < mb) sb = mb;
+        Myers<NW> s;
+        myers_init_hw<NW>(s, T.qlen);
+        for (u64 p = sb; p < oe; ++p) {
+            myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(B.bases + p) * NW, 0);
+            if (p >= ob && s.score == d) {
+                if (!f(p)) return;
+            }
+        }
+    }
+}
+
+// mid_n: [n_reads][n_adapters] number of regions (0 if the thresholds fail)
+template <int NW>
+__global__ void __launch_bounds__(RES_THREADS)
+k_mid_count(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
+            const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off,
+            const ChunkEntry *__restrict__ chunks, u32 n_chunks,
+            const uint8_t *__restrict__ chunk_min, u32 *__restrict__ mid_n, u64 *scratch,
+            u64 scratch_stride) {
+    const DevAdapter A = C.ad[a];
+    const AdapterTables T = adapter_tables(C, a);
+    const u64 tid = (u64)blockIdx.x * RES_THREADS + threadIdx.x;
+    for (u32 r = (u32)tid; r < B.n_reads; r += gridDim.x * RES_THREADS) {
+        const u32 bd = best_mid[(u64)r * n_adapters + a];
+        if (bd == 0xffffffffu) continue;
+        const int d = (int)bd;
+        const u64 mb = B.offsets[r] + (u64)end_len;
+        u32 count = 0;
+        bool ok = true;
+        mid_for_each_end<NW>(B, T, A, a, end_len, r, d, chunk_off, chunks, n_chunks, chunk_min,
+                             [&](u64 p) {
+                                 if (count == 0) {
+                                     const u64 s0 = shw_start<NW>(T, B.bases, mb, p, d);
+                                     const int alen = nw_traceback_len<NW>(T, B.bases, s0, p,
+                                                                           scratch + tid, scratch_stride);
+                                     if (alen - d < A.thr_mid) { ok = false; return false; }
+                                 }
+                                 ++count;
+                                 return true;
+                             });
+        mid_n[(u64)r * n_adapters + a] = ok ? count : 0u;
+    }
+}
+
+// pool: Region {ts, te} per location (T.cpp:1247-1258), at mid_off[r*A+a] .. + mid_n
+template <int NW>
+__global__ void __launch_bounds__(RES_THREADS)
+k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int extra_len, int n_adapters,
+           const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off,
+           const ChunkEntry *__restrict__ chunks, u32 n_chunks,
+           const uint8_t *__restrict__ chunk_min, const u32 *__restrict__ mid_n,
+           const u32 *__restrict__ mid_off, Region *__restrict__ pool,
+           const u32 *__restrict__ dev_status) {
+    if (*dev_status != DEV_STATUS_OK) return;
+    const DevAdapter A = C.ad[a];
+    const AdapterTables T = adapter_tables(C, a);
+    for (u32 r = blockIdx.x * RES_THREADS + threadIdx.x; r < B.n_reads;
+         r += gridDim.x * RES_THREADS) {
+        const u64 key = (u64)r * n_adapters + a;
+        const u32 n = mid_n[key];
+        if (n == 0) continue;
+        const int d = (int)best_mid[key];
+        const u64 rs = B.offsets[r];
+        const int tLen = (int)(B.offsets[r + 1] - rs);
+        const u64 mb = rs + (u64)end_len;
+        Region *out = pool + mid_off[key];
+        u32 i = 0;
+        mid_for_each_end<NW>(B, T, A, a, end_len, r, d, chunk_off, chunks, n_chunks, chunk_min,
+                             [&](u64 p) {
+                                 const u64 s0 = shw_start<NW>(T, B.bases, mb, p, d);
+                                 int ts = (int)(s0 - rs) - extra_len;       // T.cpp:1248,1253
+                                 int te = (int)(p - rs) + 1 + extra_len;    // T.cpp:1249,1254
+                                 if (ts < 0) ts = 0;
+                                 if (te > tLen) te = tLen;
+                                 out[i].s = ts;
+                                 out[i].e = te;
+                                 ++i;
+                                 return i < n;
+                             });
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_ends: 5' and 3' windows (T.cpp:1266-1321).  One thread per (read, adapter, side).
+// out: end_n [n_reads][n_adapters][2] location counts (0 if thresholds fail),
+//      end_pos[n_reads][n_adapters][2]: side 0 -> max te (region {0, te}), side 1 -> min ts.
+// ---------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(RES_THREADS)
+k_ends(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
+       const int *__restrict__ read_active, int *__restrict__ end_n, int *__restrict__ end_pos,
+       u64 *scratch, u64 scratch_stride) {
+    const DevAdapter A = C.ad[a];
+    const AdapterTables T = adapter_tables(C, a);
+    const u64 tid = (u64)blockIdx.x * RES_THREADS + threadIdx.x;
+    const u64 total = (u64)B.n_reads * 2;
+    for (u64 w = tid; w < total; w += (u64)gridDim.x * RES_THREADS) {
+        const u32 r = (u32)(w >> 1);
+        const int side = (int)(w & 1);
+        const u64 oidx = ((u64)r * n_adapters + a) * 2 + side;
+        int n_loc = 0, pos = 0;
+        if (read_active[r] && A.k_end > 0) {
+            const u64 rs = B.offsets[r];
+            const int tLen = (int)(B.offsets[r + 1] - rs);
+            int checkLen = end_len + A.end_extra; // T.cpp:1267
+            if (checkLen > tLen) checkLen = tLen;
+            if (checkLen >= 5) {
+                const u64 lo = side == 0 ? rs : rs + (u64)(tLen - checkLen);
+                const u64 hi = lo + (u64)checkLen;
+                const int d = hw_best<NW>(T, B.bases, lo, hi, A.k_end);
+                if (d != 0x7fffffff) {
+                    Myers<NW> s;
+                    myers_init_hw<NW>(s, T.qlen);
+                    bool ok = true;
+                    int best_pos = side == 0 ? 0 : 0x7fffffff;
+                    for (u64 p = lo; p < hi && ok; ++p) {
+                        myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(B.bases + p) * NW, 0);
+                        if (s.score != d) continue;
+                        u64 s0 = 0;
+                        if (n_loc == 0 || side == 1) s0 = shw_start<NW>(T, B.bases, lo, p, d);
+                        if (n_loc == 0) {
+                            const int alen = nw_traceback_len<NW>(T, B.bases, s0, p, scratch + tid,
+                                                                  scratch_stride);
+                            if (alen - d < A.thr_end) { ok = false; break; }
+                        }
+                        ++n_loc;
+                        if (side == 0) best_pos = (int)(p - rs) + 1;                // te, T.cpp:1286
+                        else best_pos = min(best_pos, (int)(s0 - rs));              // ts, T.cpp:1310
+                    }
+                    if (!ok) n_loc = 0;
+                    pos = best_pos;
+                }
+            }
+        }
+        end_n[oidx] = n_loc;
+        end_pos[oidx] = pos;
+    }
+}

@@ -1,0 +1,236 @@
+// K3 building blocks: Myers/Hyyro bit-vector edit distance, multi-word in registers.
+//
+// Replaces include/edlib.cpp's calculateBlock (E.cpp:409-444), myersCalcEditDistanceSemiGlobal
+// (E.cpp:547-704, HW and SHW modes), myersCalcEditDistanceNW (E.cpp:730-931) and
+// obtainAlignmentTraceback (E.cpp:945-1144) with the equivalent specification validated in
+// SURVEY.md §3.5 / tests/test_oracle_vs_ref.py: plain semi-global DP semantics, all end columns
+// with the best distance, smallest start per end, traceback priority Up > Left > Diagonal.
+//
+// Layouts.  HW scans use a TOP-padded pattern: the 64*NW-bit column holds W = 64*NW - q wildcard
+// rows in bits [0,W) (they match every byte and start with vertical delta 0, i.e. "the target has
+// an unbounded prefix that only wildcards can consume") followed by the q query rows, so the
+// bottom row of the query is always bit 63 of the last word: the per-column score update is two
+// shifts by a constant and there is no column shift or tail fix-up as in edlib's bottom padding
+// (E.cpp:658-693).  SHW / NW passes (start search, traceback) are tiny and use the unpadded layout
+// with the bottom row at a run-time bit.
+#pragma once
+#include "common.cuh"
+
+template <int NW>
+struct Myers {
+    u64 Pv[NW];
+    u64 Mv[NW];
+    int score;
+};
+
+// State "before column 0" of an HW scan in the top-padded layout.
+template <int NW>
+static __device__ __forceinline__ void myers_init_hw(Myers<NW> &s, int qlen) {
+    const int W = 64 * NW - qlen; // 0..63
+    s.Pv[0] = (W == 0) ? ~0ull : (~0ull << W);
+    s.Mv[0] = 0;
+#pragma unroll
+    for (int w = 1; w < NW; ++w) {
+        s.Pv[w] = ~0ull;
+        s.Mv[w] = 0;
+    }
+    s.score = qlen;
+}
+
+// State before column 0 of an SHW / NW pass (unpadded): H[i][-1] = i.
+template <int NW>
+static __device__ __forceinline__ void myers_init_plain(Myers<NW> &s, int qlen) {
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        s.Pv[w] = ~0ull;
+        s.Mv[w] = 0;
+    }
+    s.score = qlen;
+}
+
+// One column.  HIN = horizontal delta entering the top row: 0 for HW (free leading gap), +1 for
+// SHW / NW.  TOPBIT: the query's bottom row is bit 63 of the last word (HW layout); otherwise it is
+// bit `lastbit` of the last word.  Same recurrences as calculateBlock (E.cpp:409-444).
+template <int NW, int HIN, bool TOPBIT>
+static __device__ __forceinline__ void myers_step(Myers<NW> &s, const u64 *__restrict__ eq,
+                                                  int lastbit) {
+    int hin = HIN;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        u64 Eq = eq[w];
+        const u64 Pv = s.Pv[w], Mv = s.Mv[w];
+        const u64 hinNeg = (hin < 0) ? 1ull : 0ull;
+        const u64 Xv = Eq | Mv;
+        Eq |= hinNeg;
+        const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        u64 Ph = Mv | ~(Xh | Pv);
+        u64 Mh = Pv & Xh;
+        int hout;
+        if (w == NW - 1) {
+            if (TOPBIT) {
+                hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+            } else {
+                hout = (int)((Ph >> lastbit) & 1ull) - (int)((Mh >> lastbit) & 1ull);
+            }
+            s.score += hout;
+        } else {
+            hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+        }
+        Ph = (Ph << 1) | ((hin > 0) ? 1ull : 0ull);
+        Mh = (Mh << 1) | hinNeg;
+        s.Pv[w] = Mh | ~(Xv | Ph);
+        s.Mv[w] = Ph & Xv;
+        hin = hout;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small-window helpers used by the resolve kernels (one thread per window; byte loads).
+// ---------------------------------------------------------------------------------------------
+
+struct AdapterTables {
+    const u64 *hw; // [256][NW] top-padded
+    const u64 *fw; // [256][NW] forward, unpadded
+    const u64 *rv; // [256][NW] reversed query, unpadded
+    int qlen;
+};
+
+// Best HW distance <= k over target[lo, hi) (absolute byte offsets); INT_MAX if none.
+template <int NW>
+static __device__ int hw_best(const AdapterTables &T, const uint8_t *__restrict__ bases, u64 lo,
+                              u64 hi, int k) {
+    Myers<NW> s;
+    myers_init_hw<NW>(s, T.qlen);
+    int best = 0x7fffffff;
+    for (u64 p = lo; p < hi; ++p) {
+        const u64 *eq = T.hw + (u32)__ldg(bases + p) * NW;
+        myers_step<NW, 0, true>(s, eq, 0);
+        best = min(best, s.score);
+    }
+    return best <= k ? best : 0x7fffffff;
+}
+
+// Smallest start s (absolute) with NW(query, target[s..e]) == d, for a window starting at wlo.
+// Reversed-query SHW over target[e], target[e-1], ...; last column whose score is d
+// (E.cpp:246-256).
+template <int NW>
+static __device__ u64 shw_start(const AdapterTables &T, const uint8_t *__restrict__ bases, u64 wlo,
+                                u64 e, int d) {
+    Myers<NW> s;
+    myers_init_plain<NW>(s, T.qlen);
+    const int lastbit = (T.qlen - 1) & 63;
+    u64 avail = e - wlo + 1;
+    int ncols = (int)min(avail, (u64)(T.qlen + d));
+    int last = 0;
+    for (int j = 0; j < ncols; ++j) {
+        const u64 *eq = T.rv + (u32)__ldg(bases + (e - (u64)j)) * NW;
+        myers_step<NW, 1, false>(s, eq, lastbit);
+        if (s.score == d) last = j;
+    }
+    return e - (u64)last;
+}
+
+// Cell value H(i, j) of the stored NW matrix, j >= 1 (1-based prefix lengths), 0 <= i <= q.
+template <int NW>
+static __device__ __forceinline__ int nw_cell(const u64 *Pv, const u64 *Mv, int bottom, int i,
+                                              int qlen) {
+    // rows i+1..q  <->  bits i..q-1
+    int v = bottom;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int lo = max(i - 64 * w, 0);
+        const int hi = min(qlen - 64 * w, 64);
+        if (lo < hi) {
+            u64 m = (hi == 64 ? ~0ull : ((1ull << hi) - 1ull)) & ~((lo == 0) ? 0ull : ((1ull << lo) - 1ull));
+            v -= __popcll(Pv[w] & m);
+            v += __popcll(Mv[w] & m);
+        }
+    }
+    return v;
+}
+
+// alignmentLength of NW(query, target[s0..e0]) traced back Up > Left > Diagonal
+// (E.cpp:1023/1057/1088).  scratch: per-thread column store, element (col, k) at
+// scratch[(col * (2*NW+1) + k) * stride + tid]; must hold tl = e0 - s0 + 1 columns.
+template <int NW>
+static __device__ int nw_traceback_len(const AdapterTables &T, const uint8_t *__restrict__ bases,
+                                       u64 s0, u64 e0, u64 *scratch, u64 stride) {
+    const int q = T.qlen;
+    const int tl = (int)(e0 - s0 + 1);
+    const int lastbit = (q - 1) & 63;
+    const int REC = 2 * NW + 1;
+    Myers<NW> s;
+    myers_init_plain<NW>(s, q);
+    for (int j = 0; j < tl; ++j) {
+        const u64 *eq = T.fw + (u32)__ldg(bases + s0 + (u64)j) * NW;
+        myers_step<NW, 1, false>(s, eq, lastbit);
+        u64 *rec = scratch + (u64)j * REC * stride;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            rec[(u64)(2 * w) * stride] = s.Pv[w];
+            rec[(u64)(2 * w + 1) * stride] = s.Mv[w];
+        }
+        rec[(u64)(2 * NW) * stride] = (u64)(u32)s.score;
+    }
+    // walk
+    int i = q, j = tl, len = 0;
+    u64 cP[NW], cM[NW], lP[NW], lM[NW];
+    int cBottom, lBottom = 0;
+    auto load_col = [&](int col1, u64 *P, u64 *M, int &bottom) { // col1: 1-based column
+        const u64 *rec = scratch + (u64)(col1 - 1) * REC * stride;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            P[w] = rec[(u64)(2 * w) * stride];
+            M[w] = rec[(u64)(2 * w + 1) * stride];
+        }
+        bottom = (int)(u32)rec[(u64)(2 * NW) * stride];
+    };
+    load_col(j, cP, cM, cBottom);
+    if (j >= 2) load_col(j - 1, lP, lM, lBottom);
+    int cur = cBottom;
+    while (true) {
+        if (i == 0) { len += j; break; }
+        if (j == 0) { len += i; break; }
+        // vertical delta of row i in column j = bit i-1
+        const int w = (i - 1) >> 6, b = (i - 1) & 63;
+        int dv = 0;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww)
+            if (ww == w) dv = (int)((cP[ww] >> b) & 1ull) - (int)((cM[ww] >> b) & 1ull);
+        if (dv == 1) { // up + 1 == cur
+            cur -= 1;
+            i -= 1;
+            len += 1;
+            continue;
+        }
+        const int left = (j == 1) ? i : nw_cell<NW>(lP, lM, lBottom, i, q);
+        int ni = i, ncur;
+        if (left + 1 == cur) {
+            ncur = left;
+        } else {
+            int dl;
+            if (j == 1) {
+                dl = 1; // H(i,0) - H(i-1,0)
+            } else {
+                dl = 0;
+#pragma unroll
+                for (int ww = 0; ww < NW; ++ww)
+                    if (ww == w) dl = (int)((lP[ww] >> b) & 1ull) - (int)((lM[ww] >> b) & 1ull);
+            }
+            ncur = left - dl;
+            ni = i - 1;
+        }
+        // move one column to the left
+        j -= 1;
+        i = ni;
+        cur = ncur;
+        len += 1;
+        if (j >= 1) {
+#pragma unroll
+            for (int ww = 0; ww < NW; ++ww) { cP[ww] = lP[ww]; cM[ww] = lM[ww]; }
+            cBottom = lBottom;
+            if (j >= 2) load_col(j - 1, lP, lM, lBottom);
+        }
+    }
+    return len;
+}

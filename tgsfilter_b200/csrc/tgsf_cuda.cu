@@ -1,0 +1,1034 @@
+// libtgsf_cuda: C-ABI (include/tgsf.h) over the sm_100a kernels.  Host side = context, slot ring,
+// buffer management and the launch sequence that replaces one batch worth of
+// TGSFilterTask::filter_sequence iterations (T.cpp:1939-2061).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "adapters.cuh"
+#include "common.cuh"
+#include "kmer.cuh"
+#include "prepass.cuh"
+#include "regions.cuh"
+#include "scan.cuh"
+#include "util.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+#define CU(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            set_err("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+            return TGSF_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define TRY(call)              \
+    do {                       \
+        int rc_ = (call);      \
+        if (rc_ != TGSF_OK) return rc_; \
+    } while (0)
+
+// A growable device buffer.
+struct DBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return TGSF_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_err("cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+            return TGSF_ERR_NOMEM;
+        }
+        cap = want;
+        return TGSF_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return (T *)p; }
+};
+
+struct HBuf { // pinned host
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return TGSF_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            set_err("cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+            return TGSF_ERR_NOMEM;
+        }
+        cap = want;
+        return TGSF_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// Adapter tables on the device (shared by the context, the pre-pass and tgsf_align_hw).
+struct AdapterSet {
+    std::vector<DevAdapter> host;
+    DBuf d_ad, d_peq;
+    int max_q = 0, min_q = 0x7fffffff, max_nw = 1;
+    int max_cols = 0; // traceback scratch columns: max(q + k)
+
+    // k_mid/k_end/thr_* are filled by the caller in `host` before upload().
+    int build(const uint8_t *const *seq, const int32_t *len, int n) {
+        host.resize((size_t)n);
+        size_t words = 0;
+        for (int a = 0; a < n; ++a) {
+            DevAdapter &A = host[(size_t)a];
+            memset(&A, 0, sizeof(A));
+            A.qlen = len[a];
+            A.nw = (len[a] + 63) / 64;
+            A.peq_off = (u32)words;
+            words += (size_t)3 * 256 * (size_t)std::max(A.nw, 1);
+            if (A.qlen > 0) {
+                max_q = std::max(max_q, A.qlen);
+                min_q = std::min(min_q, A.qlen);
+                max_nw = std::max(max_nw, A.nw);
+            }
+        }
+        std::vector<u64> peq(words, 0);
+        for (int a = 0; a < n; ++a) {
+            const DevAdapter &A = host[(size_t)a];
+            const int q = A.qlen, nw = A.nw;
+            if (q <= 0) continue;
+            const int W = 64 * nw - q;
+            u64 *hw = peq.data() + A.peq_off, *fw = hw + 256 * nw, *rv = fw + 256 * nw;
+            for (int b = 0; b < 256; ++b)
+                for (int i = 0; i < W; ++i) hw[b * nw + (i >> 6)] |= 1ull << (i & 63); // wildcards
+            for (int i = 0; i < q; ++i) {
+                const int b = seq[a][i];
+                hw[b * nw + ((W + i) >> 6)] |= 1ull << ((W + i) & 63);
+                fw[b * nw + (i >> 6)] |= 1ull << (i & 63);
+                const int br = seq[a][q - 1 - i];
+                rv[br * nw + (i >> 6)] |= 1ull << (i & 63);
+            }
+        }
+        TRY(d_peq.ensure(std::max<size_t>(words, 1) * sizeof(u64)));
+        if (words) {
+            cudaError_t e = cudaMemcpy(d_peq.p, peq.data(), words * sizeof(u64), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { set_err("peq upload: %s", cudaGetErrorString(e)); return TGSF_ERR_CUDA; }
+        }
+        return TGSF_OK;
+    }
+    int upload() {
+        max_cols = 16;
+        for (auto &A : host) max_cols = std::max(max_cols, 2 * A.qlen + 2);
+        TRY(d_ad.ensure(std::max<size_t>(host.size(), 1) * sizeof(DevAdapter)));
+        if (!host.empty()) {
+            cudaError_t e = cudaMemcpy(d_ad.p, host.data(), host.size() * sizeof(DevAdapter), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { set_err("adapter upload: %s", cudaGetErrorString(e)); return TGSF_ERR_CUDA; }
+        }
+        return TGSF_OK;
+    }
+    AdapterCtx ctx() const {
+        AdapterCtx c;
+        c.ad = d_ad.as<DevAdapter>();
+        c.peq_pool = d_peq.as<u64>();
+        return c;
+    }
+    void release() { d_ad.release(); d_peq.release(); }
+};
+
+// Per-thread traceback scratch: RES grid is fixed so that the scratch is bounded.
+struct Scratch {
+    DBuf buf;
+    u64 stride = 0;
+    int ensure(u64 threads, int max_cols, int max_nw) {
+        stride = threads;
+        return buf.ensure((size_t)threads * (size_t)max_cols * (size_t)(2 * max_nw + 1) * sizeof(u64));
+    }
+};
+
+struct DevHeader { // small block mirrored to the host with every batch
+    u32 status;
+    u32 tmp_cursor;  // total pieces
+    u32 sort_cursor;
+    u32 pad;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+    cudaEvent_t ev_stage[TGSF_N_STAGES + 1] = {};
+    bool busy = false;
+    // input
+    DBuf in_bases, in_quals, in_offsets;
+    DevBatch B{};
+    u64 n_bases = 0;
+    bool has_qual = false;
+    // work arrays
+    DBuf seg_start, seg_len, seg_sum, seg_flag, tile_cnt, tile_off, tiles;
+    DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min;
+    DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
+    DBuf scan_tmp;
+    Scratch scratch;
+    u32 pool_cap = 0, pieces_cap = 0, chunks_cap = 0, tiles_cap = 0;
+    // host results
+    HBuf h_res, h_pieces, h_header;
+    u32 h_pieces_copied = 0;
+    float kernel_ms = 0, total_ms = 0;
+};
+
+}  // namespace
+
+struct tgsf_ctx {
+    int device = 0;
+    int sm_count = TGSF_SM_COUNT_FALLBACK;
+    DevParams P{};
+    AdapterSet ads;
+    DBuf counters;
+    std::vector<Slot> slots;
+    u32 head = 0, tail = 0, outstanding = 0; // ring: submit at head, collect at tail
+    u64 launches = 0;
+    float last_kernel_ms = 0, last_total_ms = 0;
+    float last_stage_ms[TGSF_N_STAGES] = {};
+};
+
+namespace {
+
+inline u32 cdiv(u64 a, u64 b) { return (u32)((a + b - 1) / b); }
+
+// exclusive scan of in[0..n) -> out[0..n], out[n] = total.  tmp: scratch u32 array.
+int exclusive_scan(tgsf_ctx *c, cudaStream_t st, const u32 *in, u32 *out, u32 n, u32 *tmp, size_t tmp_words) {
+    if (n == 0) {
+        CU(cudaMemsetAsync(out, 0, sizeof(u32), st));
+        return TGSF_OK;
+    }
+    const u32 nb = cdiv(n, SCANB_TILE);
+    if ((size_t)nb * 2 + 8 > tmp_words) { set_err("scan scratch too small"); return TGSF_ERR_INVALID; }
+    u32 *sums = tmp;               // nb
+    u32 *sums_sc = tmp + nb;       // nb + 1
+    u32 *rest = tmp + 2 * (size_t)nb + 1;
+    k_scan_block<<<nb, UTIL_THREADS, 0, st>>>(in, out, n, sums);
+    c->launches++;
+    if (nb == 1) { // single block: its total is the grand total
+        CU(cudaMemcpyAsync(out + n, sums, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        return TGSF_OK;
+    }
+    TRY(exclusive_scan(c, st, sums, sums_sc, nb, rest, tmp_words - (2 * (size_t)nb + 1)));
+    k_scan_add<<<cdiv(n, UTIL_THREADS), UTIL_THREADS, 0, st>>>(out, n, sums_sc, sums_sc + nb);
+    c->launches++;
+    return TGSF_OK;
+}
+
+int slot_init(Slot &s) {
+    CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&s.ev_start));
+    CU(cudaEventCreate(&s.ev_k0));
+    CU(cudaEventCreate(&s.ev_k1));
+    CU(cudaEventCreate(&s.ev_end));
+    for (auto &e : s.ev_stage) CU(cudaEventCreate(&e));
+    return TGSF_OK;
+}
+
+void slot_release(Slot &s) {
+    DBuf *bufs[] = {&s.in_bases, &s.in_quals, &s.in_offsets, &s.seg_start, &s.seg_len, &s.seg_sum,
+                    &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
+                    &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min,
+                    &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
+                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.scratch.buf};
+    for (DBuf *b : bufs) b->release();
+    s.h_res.release();
+    s.h_pieces.release();
+    s.h_header.release();
+    if (s.ev_start) cudaEventDestroy(s.ev_start);
+    if (s.ev_k0) cudaEventDestroy(s.ev_k0);
+    if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+    if (s.ev_end) cudaEventDestroy(s.ev_end);
+    for (auto &e : s.ev_stage)
+        if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+}
+
+// Size every work array for a batch of n reads / n_bases bases.
+int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
+    const int A = std::max(c->P.n_adapters, 1);
+    if (s.pool_cap == 0) s.pool_cap = 65536;
+    s.pieces_cap = n + s.pool_cap;
+    s.chunks_cap = (u32)(n_bases / MID_CHUNK + 2ull * n + 16);
+    s.tiles_cap = (u32)(n_bases / SCAN_TILE + (u64)s.pieces_cap + 16);
+    const size_t nseg = std::max<size_t>(n, s.pieces_cap) + 1;
+    TRY(s.seg_start.ensure(nseg * sizeof(u64)));
+    TRY(s.seg_len.ensure(nseg * sizeof(int)));
+    TRY(s.seg_sum.ensure(nseg * sizeof(u64)));
+    TRY(s.seg_flag.ensure(nseg * sizeof(int)));
+    TRY(s.tile_cnt.ensure(nseg * sizeof(u32)));
+    TRY(s.tile_off.ensure((nseg + 1) * sizeof(u32)));
+    TRY(s.tiles.ensure((size_t)s.tiles_cap * sizeof(TileEntry)));
+    TRY(s.read_active.ensure(((size_t)n + 1) * sizeof(int)));
+    TRY(s.piece_cnt.ensure(((size_t)n + 1) * sizeof(u32)));
+    TRY(s.piece_begin.ensure(((size_t)n + 2) * sizeof(u32)));
+    TRY(s.chunk_cnt.ensure(((size_t)n + 1) * sizeof(u32)));
+    TRY(s.chunk_off.ensure(((size_t)n + 2) * sizeof(u32)));
+    TRY(s.chunks.ensure((size_t)s.chunks_cap * sizeof(ChunkEntry)));
+    TRY(s.chunk_min.ensure((size_t)s.chunks_cap * (size_t)A));
+    TRY(s.best_mid.ensure(((size_t)n * A + 1) * sizeof(u32)));
+    TRY(s.mid_n.ensure(((size_t)n * A + 1) * sizeof(u32)));
+    TRY(s.mid_off.ensure(((size_t)n * A + 2) * sizeof(u32)));
+    TRY(s.end_n.ensure(((size_t)n * A * 2 + 1) * sizeof(int)));
+    TRY(s.end_pos.ensure(((size_t)n * A * 2 + 1) * sizeof(int)));
+    TRY(s.pool.ensure((size_t)s.pool_cap * sizeof(Region)));
+    TRY(s.sortbuf.ensure((size_t)s.pool_cap * 5 * sizeof(Region)));
+    TRY(s.tmp.ensure((size_t)s.pieces_cap * sizeof(TmpPiece)));
+    TRY(s.pieces.ensure((size_t)s.pieces_cap * sizeof(tgsf_piece)));
+    TRY(s.res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
+    TRY(s.header.ensure(sizeof(DevHeader)));
+    const size_t scan_words = 4 * (std::max<size_t>(nseg, (size_t)n * A) / SCANB_TILE) + 4096;
+    TRY(s.scan_tmp.ensure(scan_words * sizeof(u32)));
+    TRY(s.h_res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
+    TRY(s.h_pieces.ensure(((size_t)n + 4096) * sizeof(tgsf_piece)));
+    TRY(s.h_header.ensure(sizeof(DevHeader)));
+    const u64 res_threads = (u64)c->sm_count * 4 * RES_THREADS;
+    TRY(s.scratch.ensure(res_threads, c->ads.max_cols, c->ads.max_nw));
+    return TGSF_OK;
+}
+
+template <typename F>
+int for_nw(int nw, F f) {
+    switch (nw) {
+        case 1: return f(std::integral_constant<int, 1>());
+        case 2: return f(std::integral_constant<int, 2>());
+        case 3: return f(std::integral_constant<int, 3>());
+        case 4: return f(std::integral_constant<int, 4>());
+        default: set_err("adapter longer than %d", TGSF_MAX_ADAPTER_LEN); return TGSF_ERR_INVALID;
+    }
+}
+
+int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_err("launch %s: %s", what, cudaGetErrorString(e));
+        return TGSF_ERR_CUDA;
+    }
+    return TGSF_OK;
+}
+
+// K1 over a segment list (raw reads or kept pieces) + tile table construction.
+int launch_scan_pass(tgsf_ctx *c, Slot &s, u32 n_seg, u64 *bin_cnt, u64 *bin_qual) {
+    cudaStream_t st = s.stream;
+    const size_t scan_words = s.scan_tmp.cap / sizeof(u32);
+    TRY(exclusive_scan(c, st, s.tile_cnt.as<u32>(), s.tile_off.as<u32>(), n_seg, s.scan_tmp.as<u32>(), scan_words));
+    if (n_seg) {
+        k_fill_tiles<<<cdiv(n_seg, 256), 256, 0, st>>>(s.tile_off.as<u32>(), n_seg, s.tiles.as<TileEntry>());
+        c->launches++;
+    }
+    // the tile count lives on the device; the persistent grid reads it through tile_off[n_seg]
+    const int grid = c->sm_count;
+    u32 *status = &s.header.as<DevHeader>()->status;
+    // n_tiles is passed by value through a tiny indirection kernel-free trick: tiles_cap bounds it,
+    // and the kernel takes the device-side total.
+    if (s.has_qual) {
+        k_scan_tiles_dyn<true><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(
+            s.B.bases, s.B.quals, s.tiles.as<TileEntry>(), s.tile_off.as<u32>() + n_seg,
+            s.seg_start.as<u64>(), s.seg_len.as<int>(), s.seg_sum.as<u64>(), bin_cnt, bin_qual,
+            c->P.qtype, c->P.L.max_bins, status);
+    } else {
+        k_scan_tiles_dyn<false><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(
+            s.B.bases, s.B.quals, s.tiles.as<TileEntry>(), s.tile_off.as<u32>() + n_seg,
+            s.seg_start.as<u64>(), s.seg_len.as<int>(), s.seg_sum.as<u64>(), bin_cnt, bin_qual,
+            c->P.qtype, c->P.L.max_bins, status);
+    }
+    c->launches++;
+    return check_launch("k_scan_tiles");
+}
+
+int launch_ends_qc(tgsf_ctx *c, Slot &s, u32 n_seg, const int *flag, bool clean) {
+    if (c->P.bc_len <= 0 || n_seg == 0) return TGSF_OK;
+    u64 *C = c->counters.as<u64>();
+    const tgsf_counter_layout &L = c->P.L;
+    u64 *cnt5 = C + (clean ? L.clean5p_cnt : L.raw5p_cnt), *q5 = C + (clean ? L.clean5p_qual : L.raw5p_qual);
+    u64 *cnt3 = C + (clean ? L.clean3p_cnt : L.raw3p_cnt), *q3 = C + (clean ? L.clean3p_qual : L.raw3p_qual);
+    const int grid = std::min<u32>((u32)c->sm_count * 4, cdiv(n_seg, ENDS_THREADS / 32));
+    const size_t sm = c->P.bc_len <= ENDS_SMEM_ROWS ? (size_t)2 * c->P.bc_len * 10 * sizeof(u32) : 0;
+    if (s.has_qual)
+        k_ends_qc<true><<<grid, ENDS_THREADS, sm, s.stream>>>(s.B.bases, s.B.quals, n_seg, s.seg_start.as<u64>(),
+                                                              s.seg_len.as<int>(), flag, c->P.bc_len, c->P.qtype,
+                                                              cnt5, q5, cnt3, q3);
+    else
+        k_ends_qc<false><<<grid, ENDS_THREADS, sm, s.stream>>>(s.B.bases, s.B.quals, n_seg, s.seg_start.as<u64>(),
+                                                               s.seg_len.as<int>(), flag, c->P.bc_len, c->P.qtype,
+                                                               cnt5, q5, cnt3, q3);
+    c->launches++;
+    return check_launch("k_ends_qc");
+}
+
+// Everything up to (and including) the pool-size check: raw QC, quality band, K3 scans + counts.
+int launch_head(tgsf_ctx *c, Slot &s) {
+    cudaStream_t st = s.stream;
+    const u32 n = s.B.n_reads;
+    const int A = c->P.n_adapters;
+    u64 *C = c->counters.as<u64>();
+    const tgsf_counter_layout &L = c->P.L;
+    DevParams P = c->P;
+    P.has_qual = s.has_qual;
+    CU(cudaMemsetAsync(s.header.p, 0, sizeof(DevHeader), st));
+    u32 *status = &s.header.as<DevHeader>()->status;
+    if (n == 0) {
+        for (int i = 0; i <= 4; ++i) CU(cudaEventRecord(s.ev_stage[i], st));
+        return TGSF_OK;
+    }
+
+    CU(cudaEventRecord(s.ev_stage[0], st));
+    k_read_segments<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.seg_start.as<u64>(), s.seg_len.as<int>(),
+                                                  s.seg_sum.as<u64>(), s.tile_cnt.as<u32>(), L.max_bins, status);
+    c->launches++;
+    TRY(launch_scan_pass(c, s, n, C + L.raw_bin_cnt, C + L.raw_bin_qual));
+    CU(cudaEventRecord(s.ev_stage[1], st));
+    if (s.has_qual)
+        k_finalize_raw<true><<<cdiv(n, REG_THREADS), REG_THREADS, 0, st>>>(
+            s.B, P, s.seg_sum.as<u64>(), s.res.as<tgsf_read_result>(), s.read_active.as<int>(),
+            s.piece_cnt.as<u32>(), C);
+    else
+        k_finalize_raw<false><<<cdiv(n, REG_THREADS), REG_THREADS, 0, st>>>(
+            s.B, P, s.seg_sum.as<u64>(), s.res.as<tgsf_read_result>(), s.read_active.as<int>(),
+            s.piece_cnt.as<u32>(), C);
+    c->launches++;
+    TRY(launch_ends_qc(c, s, n, nullptr, false));
+    CU(cudaEventRecord(s.ev_stage[2], st));
+
+    const bool filter = (P.flags & TGSF_FLAG_FILTER) != 0;
+    if (filter && A > 0) {
+        k_count_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.read_active.as<int>(), P.end_len, c->ads.min_q,
+                                                     s.chunk_cnt.as<u32>(), s.best_mid.as<u32>(),
+                                                     s.mid_n.as<u32>(), A);
+        c->launches++;
+        TRY(exclusive_scan(c, st, s.chunk_cnt.as<u32>(), s.chunk_off.as<u32>(), n, s.scan_tmp.as<u32>(),
+                           s.scan_tmp.cap / sizeof(u32)));
+        k_fill_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.chunk_off.as<u32>(), P.end_len, s.chunks.as<ChunkEntry>());
+        c->launches++;
+        const AdapterCtx AC = c->ads.ctx();
+        const u32 *n_chunks_ptr = s.chunk_off.as<u32>() + n;
+        const int res_grid = c->sm_count * 4;
+        for (int a = 0; a < A; ++a) {
+            const DevAdapter &Ah = c->ads.host[(size_t)a];
+            if (Ah.k_mid <= 0) continue;
+            TRY(for_nw(Ah.nw, [&](auto nwc) {
+                constexpr int NW = decltype(nwc)::value;
+                k_mid_scan_dyn<NW><<<c->sm_count * 8, MID_THREADS, 256 * NW * sizeof(u64), st>>>(
+                    s.B, AC, a, P.end_len, s.chunks.as<ChunkEntry>(), n_chunks_ptr, s.chunks_cap,
+                    s.chunk_min.as<uint8_t>(), s.best_mid.as<u32>(), A);
+                c->launches++;
+                return check_launch("k_mid_scan");
+            }));
+        }
+        CU(cudaEventRecord(s.ev_stage[3], st));
+        for (int a = 0; a < A; ++a) {
+            const DevAdapter &Ah = c->ads.host[(size_t)a];
+            TRY(for_nw(Ah.nw, [&](auto nwc) {
+                constexpr int NW = decltype(nwc)::value;
+                if (Ah.k_mid > 0) {
+                    k_mid_count<NW><<<res_grid, RES_THREADS, 0, st>>>(
+                        s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
+                        s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.mid_n.as<u32>(),
+                        s.scratch.buf.as<u64>(), s.scratch.stride);
+                    c->launches++;
+                }
+                k_ends<NW><<<res_grid, RES_THREADS, 0, st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
+                                                            s.end_n.as<int>(), s.end_pos.as<int>(),
+                                                            s.scratch.buf.as<u64>(), s.scratch.stride);
+                c->launches++;
+                return check_launch("k3 resolve");
+            }));
+        }
+        TRY(exclusive_scan(c, st, s.mid_n.as<u32>(), s.mid_off.as<u32>(), n * (u32)A, s.scan_tmp.as<u32>(),
+                           s.scan_tmp.cap / sizeof(u32)));
+        k_check_pool<<<1, 1, 0, st>>>(s.mid_off.as<u32>() + (size_t)n * A, s.pool_cap, status);
+        c->launches++;
+    } else {
+        CU(cudaEventRecord(s.ev_stage[3], st));
+    }
+    CU(cudaEventRecord(s.ev_stage[4], st));
+    return check_launch("head");
+}
+
+// From the region pool onwards; re-runnable after a pool overflow (touches no counter before the
+// overflow check has passed).
+int launch_tail(tgsf_ctx *c, Slot &s) {
+    cudaStream_t st = s.stream;
+    const u32 n = s.B.n_reads;
+    const int A = c->P.n_adapters;
+    u64 *C = c->counters.as<u64>();
+    const tgsf_counter_layout &L = c->P.L;
+    DevParams P = c->P;
+    P.has_qual = s.has_qual;
+    DevHeader *H = s.header.as<DevHeader>();
+    if (n == 0) {
+        for (int i = 5; i <= TGSF_N_STAGES; ++i) CU(cudaEventRecord(s.ev_stage[i], st));
+        return TGSF_OK;
+    }
+    const bool filter = (P.flags & TGSF_FLAG_FILTER) != 0;
+    const AdapterCtx AC = c->ads.ctx();
+    const int res_grid = c->sm_count * 4;
+    if (filter && A > 0) {
+        for (int a = 0; a < A; ++a) {
+            const DevAdapter &Ah = c->ads.host[(size_t)a];
+            if (Ah.k_mid <= 0) continue;
+            TRY(for_nw(Ah.nw, [&](auto nwc) {
+                constexpr int NW = decltype(nwc)::value;
+                k_mid_emit<NW><<<res_grid, RES_THREADS, 0, st>>>(
+                    s.B, AC, a, P.end_len, P.extra_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
+                    s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.mid_n.as<u32>(),
+                    s.mid_off.as<u32>(), s.pool.as<Region>(), &H->status);
+                c->launches++;
+                return check_launch("k_mid_emit");
+            }));
+        }
+    } else if (filter) {
+        // no adapters: adapterMap still applies the fixed trims; no location arrays to read
+        CU(cudaMemsetAsync(s.mid_n.p, 0, sizeof(u32), st));
+    }
+    k_regions<<<cdiv(n, REG_THREADS), REG_THREADS, 0, st>>>(
+        s.B, P, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(), s.mid_n.as<u32>(),
+        s.mid_off.as<u32>(), s.pool.as<Region>(), s.sortbuf.as<Region>(), s.pool_cap * 5, &H->sort_cursor,
+        s.res.as<tgsf_read_result>(), s.piece_cnt.as<u32>(), s.tmp.as<TmpPiece>(), s.pieces_cap,
+        &H->tmp_cursor, C, &H->status);
+    c->launches++;
+    TRY(exclusive_scan(c, st, s.piece_cnt.as<u32>(), s.piece_begin.as<u32>(), n, s.scan_tmp.as<u32>(),
+                       s.scan_tmp.cap / sizeof(u32)));
+    const u32 place_n = std::max(n, s.pieces_cap);
+    k_place_pieces<<<cdiv(place_n, 256), 256, 0, st>>>(s.tmp.as<TmpPiece>(), &H->tmp_cursor,
+                                                       s.piece_begin.as<u32>(), s.res.as<tgsf_read_result>(),
+                                                       s.pieces.as<tgsf_piece>(), n,
+                                                       (P.flags & TGSF_FLAG_ONLY_QC) ? 1 : 0, &H->status);
+    c->launches++;
+    CU(cudaEventRecord(s.ev_stage[5], st));
+    if (!(P.flags & TGSF_FLAG_ONLY_QC)) {
+        if (P.min_repeat > 0) {
+            if (P.kmer <= 15)
+                k_kmer<u32><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
+                                                                            &H->tmp_cursor, C, &H->status);
+            else
+                k_kmer<u64><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
+                                                                            &H->tmp_cursor, C, &H->status);
+            c->launches++;
+        }
+        CU(cudaEventRecord(s.ev_stage[6], st));
+        // clean pass over the kept pieces (T.cpp:1991-2009); piece count is device-side, the
+        // kernels are launched over the capacity and bound themselves by the header.
+        k_piece_segments_dyn<<<cdiv(s.pieces_cap, 256), 256, 0, st>>>(
+            s.B, s.pieces.as<tgsf_piece>(), &H->tmp_cursor, s.pieces_cap, s.seg_start.as<u64>(),
+            s.seg_len.as<int>(), s.seg_sum.as<u64>(), s.tile_cnt.as<u32>(), &H->status);
+        c->launches++;
+        TRY(launch_scan_pass(c, s, s.pieces_cap, C + L.clean_bin_cnt, C + L.clean_bin_qual));
+        if (s.has_qual)
+            k_finalize_clean_dyn<true><<<cdiv(s.pieces_cap, REG_THREADS), REG_THREADS, 0, st>>>(
+                P, s.pieces.as<tgsf_piece>(), &H->tmp_cursor, s.pieces_cap, s.seg_sum.as<u64>(),
+                s.seg_flag.as<int>(), C, &H->status);
+        else
+            k_finalize_clean_dyn<false><<<cdiv(s.pieces_cap, REG_THREADS), REG_THREADS, 0, st>>>(
+                P, s.pieces.as<tgsf_piece>(), &H->tmp_cursor, s.pieces_cap, s.seg_sum.as<u64>(),
+                s.seg_flag.as<int>(), C, &H->status);
+        c->launches++;
+        TRY(launch_ends_qc(c, s, s.pieces_cap, s.seg_flag.as<int>(), true));
+    } else {
+        CU(cudaEventRecord(s.ev_stage[6], st));
+    }
+    CU(cudaEventRecord(s.ev_stage[7], st));
+    return check_launch("tail");
+}
+
+int enqueue_d2h(tgsf_ctx *c, Slot &s) {
+    (void)c;
+    cudaStream_t st = s.stream;
+    const u32 n = s.B.n_reads;
+    CU(cudaMemcpyAsync(s.h_header.p, s.header.p, sizeof(DevHeader), cudaMemcpyDeviceToHost, st));
+    if (n) CU(cudaMemcpyAsync(s.h_res.p, s.res.p, (size_t)n * sizeof(tgsf_read_result), cudaMemcpyDeviceToHost, st));
+    s.h_pieces_copied = std::min<u32>(s.pieces_cap, n + 4096);
+    if (s.h_pieces_copied)
+        CU(cudaMemcpyAsync(s.h_pieces.p, s.pieces.p, (size_t)s.h_pieces_copied * sizeof(tgsf_piece),
+                           cudaMemcpyDeviceToHost, st));
+    return TGSF_OK;
+}
+
+int run_pipeline(tgsf_ctx *c, Slot &s) {
+    TRY(launch_head(c, s));
+    TRY(launch_tail(c, s));
+    CU(cudaEventRecord(s.ev_k1, s.stream));
+    TRY(enqueue_d2h(c, s));
+    CU(cudaEventRecord(s.ev_end, s.stream));
+    return TGSF_OK;
+}
+
+int validate_params(const tgsf_params *p) {
+    if (!p) { set_err("params is NULL"); return TGSF_ERR_INVALID; }
+    if (p->n_adapters < 0 || p->n_adapters > TGSF_MAX_ADAPTERS) { set_err("n_adapters out of range"); return TGSF_ERR_INVALID; }
+    if (p->n_adapters > 0 && (!p->adapter_seq || !p->adapter_len)) { set_err("adapter arrays missing"); return TGSF_ERR_INVALID; }
+    for (int a = 0; a < p->n_adapters; ++a)
+        if (p->adapter_len[a] <= 0 || p->adapter_len[a] > TGSF_MAX_ADAPTER_LEN || !p->adapter_seq[a]) {
+            set_err("adapter %d has invalid length %d", a, p->adapter_len[a]);
+            return TGSF_ERR_INVALID;
+        }
+    if ((p->flags & TGSF_FLAG_FILTER) && p->n_adapters > 0 && !(p->end_sim > 0.0f && p->mid_sim > 0.0f)) {
+        set_err("end_sim / mid_sim must be > 0 when filtering");
+        return TGSF_ERR_INVALID;
+    }
+    if (p->min_repeat > 0 && (p->kmer < 1 || p->kmer > 31)) { set_err("kmer must be in [1,31]"); return TGSF_ERR_INVALID; }
+    if (p->bc_len < 0 || p->end_len < 0 || p->extra_len < 0) { set_err("negative length parameter"); return TGSF_ERR_INVALID; }
+    if (p->n_slots < 0 || p->n_slots > 4) { set_err("n_slots out of range"); return TGSF_ERR_INVALID; }
+    return TGSF_OK;
+}
+
+// Integer stand-ins for the float tests of GetEditDistance, evaluated with the same C++ float
+// expressions the reference uses.
+void fill_thresholds(DevAdapter &A, const tgsf_params *p) {
+    const int qLen = A.qlen;
+    const float endSim = p->end_sim, midSim = p->mid_sim;
+    auto min_mlen = [&](float sim, int match_len) {
+        int m = 0;
+        for (; m <= qLen; ++m) {
+            float s = static_cast<float>(m) / qLen; // T.cpp:1250 / 1287
+            if (s >= sim) break;
+        }
+        return std::max(m, match_len); // m == qLen + 1: can never pass
+    };
+    A.k_mid = std::min(qLen - p->mid_match_len + 1, qLen - 1); // T.cpp:1233
+    A.k_end = std::min(qLen - p->end_match_len + 1, qLen - 1); // T.cpp:1271
+    A.thr_mid = min_mlen(midSim, p->mid_match_len);
+    A.thr_end = min_mlen(endSim, p->end_match_len);
+    if (A.thr_mid > qLen) A.k_mid = 0;
+    if (A.thr_end > qLen) A.k_end = 0;
+    A.end_extra = endSim > 0.0f ? int(qLen / endSim) : 0; // T.cpp:1267
+    A.halo_mid = A.k_mid > 0 ? ((qLen + A.k_mid - 1 + 15) / 16) * 16 : 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" {
+
+const char *tgsf_version(void) { return "libtgsf_cuda 0.1 (sm_100a; TGSFilter v1.11 per-read path)"; }
+const char *tgsf_last_error(void) { return g_err; }
+
+int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
+    if (!out) { set_err("out is NULL"); return TGSF_ERR_INVALID; }
+    *out = nullptr;
+    TRY(validate_params(params));
+    CU(cudaSetDevice(device));
+    tgsf_ctx *c = new (std::nothrow) tgsf_ctx();
+    if (!c) return TGSF_ERR_NOMEM;
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    DevParams &P = c->P;
+    P.min_len = params->min_len;
+    P.max_len = params->max_len;
+    P.min_q = (double)params->min_q;
+    P.max_q = (double)params->max_q;
+    P.bc_len = params->bc_len;
+    P.head_trim = params->head_trim;
+    P.tail_trim = params->tail_trim;
+    P.end_len = params->end_len;
+    P.extra_len = params->extra_len;
+    P.kmer = params->kmer;
+    P.min_repeat = params->min_repeat;
+    P.qtype = params->qtype;
+    P.flags = params->flags;
+    P.n_adapters = params->n_adapters;
+    P.has_qual = 1;
+    tgsf_make_layout(params->bc_len, params->max_read_len, &P.L);
+
+    int rc = c->ads.build((const uint8_t *const *)params->adapter_seq, params->adapter_len, params->n_adapters);
+    if (rc == TGSF_OK) {
+        for (auto &A : c->ads.host) fill_thresholds(A, params);
+        rc = c->ads.upload();
+    }
+    if (rc == TGSF_OK) rc = c->counters.ensure((size_t)P.L.n_u64 * sizeof(u64));
+    if (rc == TGSF_OK && cudaMemset(c->counters.p, 0, (size_t)P.L.n_u64 * sizeof(u64)) != cudaSuccess) rc = TGSF_ERR_CUDA;
+    const int ns = params->n_slots > 0 ? params->n_slots : 2;
+    c->slots.resize((size_t)ns);
+    for (int i = 0; i < ns && rc == TGSF_OK; ++i) rc = slot_init(c->slots[(size_t)i]);
+    if (rc == TGSF_OK) {
+        cudaError_t e1 = cudaFuncSetAttribute(k_scan_tiles_dyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
+        cudaError_t e2 = cudaFuncSetAttribute(k_scan_tiles_dyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
+        cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
+        cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            set_err("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4));
+            rc = TGSF_ERR_CUDA;
+        }
+    }
+    if (rc != TGSF_OK) {
+        tgsf_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return TGSF_OK;
+}
+
+int tgsf_destroy(tgsf_ctx *c) {
+    if (!c) return TGSF_OK;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto &s : c->slots) slot_release(s);
+    c->ads.release();
+    c->counters.release();
+    delete c;
+    return TGSF_OK;
+}
+
+int tgsf_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) return TGSF_ERR_INVALID;
+    CU(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return TGSF_OK;
+}
+int tgsf_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return TGSF_OK;
+}
+
+static int submit_common(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals, const u64 *offsets,
+                         u32 n_reads, u64 n_bases, bool on_device) {
+    if (!c) { set_err("ctx is NULL"); return TGSF_ERR_INVALID; }
+    if (n_reads && (!bases || !offsets)) { set_err("bases/offsets NULL"); return TGSF_ERR_INVALID; }
+    if (n_reads > (1u << 24)) { set_err("more than 2^24 reads in one batch"); return TGSF_ERR_INVALID; }
+    if (c->outstanding == c->slots.size()) { set_err("all %zu slots busy: collect first", c->slots.size()); return TGSF_ERR_STATE; }
+    CU(cudaSetDevice(c->device));
+    Slot &s = c->slots[c->head];
+    s.has_qual = quals != nullptr;
+    s.n_bases = n_bases;
+    TRY(slot_reserve(c, s, n_reads, n_bases));
+    CU(cudaEventRecord(s.ev_start, s.stream));
+    if (on_device) {
+        if (((uintptr_t)bases & 15) || ((uintptr_t)quals & 15)) { set_err("device streams must be 16-byte aligned"); return TGSF_ERR_INVALID; }
+        s.B.bases = bases;
+        s.B.quals = quals;
+        s.B.offsets = offsets;
+    } else {
+        const size_t pad = 64;
+        TRY(s.in_bases.ensure((size_t)n_bases + pad));
+        TRY(s.in_offsets.ensure(((size_t)n_reads + 1) * sizeof(u64)));
+        if (n_bases) CU(cudaMemcpyAsync(s.in_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, s.stream));
+        if (quals) {
+            TRY(s.in_quals.ensure((size_t)n_bases + pad));
+            if (n_bases) CU(cudaMemcpyAsync(s.in_quals.p, quals, (size_t)n_bases, cudaMemcpyHostToDevice, s.stream));
+        }
+        if (n_reads) CU(cudaMemcpyAsync(s.in_offsets.p, offsets, ((size_t)n_reads + 1) * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
+        s.B.bases = s.in_bases.as<uint8_t>();
+        s.B.quals = quals ? s.in_quals.as<uint8_t>() : nullptr;
+        s.B.offsets = s.in_offsets.as<u64>();
+    }
+    s.B.n_reads = n_reads;
+    CU(cudaEventRecord(s.ev_k0, s.stream));
+    TRY(run_pipeline(c, s));
+    s.busy = true;
+    c->head = (c->head + 1) % (u32)c->slots.size();
+    c->outstanding++;
+    return TGSF_OK;
+}
+
+int tgsf_submit(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets, uint32_t n_reads) {
+    if (n_reads && !offsets) { set_err("offsets NULL"); return TGSF_ERR_INVALID; }
+    const u64 n_bases = n_reads ? offsets[n_reads] : 0;
+    return submit_common(c, bases, quals, (const u64 *)offsets, n_reads, n_bases, false);
+}
+
+int tgsf_submit_device(tgsf_ctx *c, const uint8_t *d_bases, const uint8_t *d_quals, const uint64_t *d_offsets,
+                       uint32_t n_reads, uint64_t n_bases) {
+    return submit_common(c, d_bases, d_quals, (const u64 *)d_offsets, n_reads, n_bases, true);
+}
+
+int tgsf_collect(tgsf_ctx *c, tgsf_read_result *reads, uint32_t n_reads, tgsf_piece *pieces, uint32_t pieces_cap,
+                 uint32_t *n_pieces) {
+    if (!c) { set_err("ctx is NULL"); return TGSF_ERR_INVALID; }
+    if (c->outstanding == 0) { set_err("nothing outstanding"); return TGSF_ERR_STATE; }
+    CU(cudaSetDevice(c->device));
+    Slot &s = c->slots[c->tail];
+    CU(cudaEventSynchronize(s.ev_end));
+    DevHeader *H = (DevHeader *)s.h_header.p;
+    float extra_ms = 0;
+    int guard = 0;
+    while (H->status == DEV_STATUS_POOL_OVERFLOW && guard++ < 8) {
+        // grow the region pool to what k_mid_count asked for and re-run the tail
+        u32 need = 0;
+        CU(cudaMemcpy(&need, s.mid_off.as<u32>() + (size_t)s.B.n_reads * std::max(c->P.n_adapters, 1), sizeof(u32),
+                      cudaMemcpyDeviceToHost));
+        s.pool_cap = std::max(need + need / 4 + 1024, s.pool_cap * 2);
+        TRY(slot_reserve(c, s, s.B.n_reads, s.n_bases));
+        CU(cudaMemsetAsync(s.header.p, 0, sizeof(DevHeader), s.stream));
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, s.stream));
+        TRY(launch_tail(c, s));
+        CU(cudaEventRecord(e1, s.stream));
+        TRY(enqueue_d2h(c, s));
+        CU(cudaStreamSynchronize(s.stream));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        extra_ms += ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    }
+    float k_ms = 0, t_ms = 0;
+    cudaEventElapsedTime(&k_ms, s.ev_k0, s.ev_k1);
+    cudaEventElapsedTime(&t_ms, s.ev_start, s.ev_end);
+    c->last_kernel_ms = k_ms + extra_ms;
+    c->last_total_ms = t_ms + extra_ms;
+    for (int i = 0; i < TGSF_N_STAGES; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s.ev_stage[i], s.ev_stage[i + 1]);
+        c->last_stage_ms[i] = ms;
+    }
+
+    auto retire = [&]() {
+        s.busy = false;
+        c->tail = (c->tail + 1) % (u32)c->slots.size();
+        c->outstanding--;
+    };
+    if (H->status == DEV_STATUS_BIN_OVERFLOW) {
+        retire();
+        set_err("a read is longer than max_read_len allows (per-100 bp bins)");
+        return TGSF_ERR_CAPACITY;
+    }
+    if (H->status != DEV_STATUS_OK) {
+        retire();
+        set_err("device status %u", H->status);
+        return TGSF_ERR_CUDA;
+    }
+    const u32 total = H->tmp_cursor;
+    if (n_pieces) *n_pieces = total;
+    if (reads) {
+        if (n_reads < s.B.n_reads) { set_err("reads array too small"); return TGSF_ERR_CAPACITY; }
+        memcpy(reads, s.h_res.p, (size_t)s.B.n_reads * sizeof(tgsf_read_result));
+    }
+    if (pieces) {
+        if (pieces_cap < total) { set_err("pieces array too small: need %u", total); return TGSF_ERR_CAPACITY; }
+        const u32 have = std::min(total, s.h_pieces_copied);
+        memcpy(pieces, s.h_pieces.p, (size_t)have * sizeof(tgsf_piece));
+        if (total > have)
+            CU(cudaMemcpy(pieces + have, s.pieces.as<tgsf_piece>() + have, (size_t)(total - have) * sizeof(tgsf_piece),
+                          cudaMemcpyDeviceToHost));
+    }
+    retire();
+    return TGSF_OK;
+}
+
+int tgsf_last_timing(tgsf_ctx *c, float *kernel_ms, float *total_ms) {
+    if (!c) return TGSF_ERR_INVALID;
+    if (kernel_ms) *kernel_ms = c->last_kernel_ms;
+    if (total_ms) *total_ms = c->last_total_ms;
+    return TGSF_OK;
+}
+
+int tgsf_last_stage_ms(tgsf_ctx *c, float *out, int n) {
+    if (!c || !out) return TGSF_ERR_INVALID;
+    for (int i = 0; i < n && i < TGSF_N_STAGES; ++i) out[i] = c->last_stage_ms[i];
+    return TGSF_OK;
+}
+
+int tgsf_counter_layout_get(const tgsf_ctx *c, tgsf_counter_layout *out) {
+    if (!c || !out) return TGSF_ERR_INVALID;
+    *out = c->P.L;
+    return TGSF_OK;
+}
+
+int tgsf_counters(tgsf_ctx *c, uint64_t *out, uint32_t n_u64) {
+    if (!c || !out) return TGSF_ERR_INVALID;
+    if (c->outstanding) { set_err("collect all batches first"); return TGSF_ERR_STATE; }
+    if (n_u64 < c->P.L.n_u64) { set_err("counter array too small"); return TGSF_ERR_CAPACITY; }
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpy(out, c->counters.p, (size_t)c->P.L.n_u64 * sizeof(u64), cudaMemcpyDeviceToHost));
+    return TGSF_OK;
+}
+
+int tgsf_counters_reset(tgsf_ctx *c) {
+    if (!c) return TGSF_ERR_INVALID;
+    if (c->outstanding) { set_err("collect all batches first"); return TGSF_ERR_STATE; }
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemset(c->counters.p, 0, (size_t)c->P.L.n_u64 * sizeof(u64)));
+    return TGSF_OK;
+}
+
+int tgsf_counters_device(tgsf_ctx *c, void **d_ptr, uint32_t *n_u64) {
+    if (!c || !d_ptr) return TGSF_ERR_INVALID;
+    *d_ptr = c->counters.p;
+    if (n_u64) *n_u64 = c->P.L.n_u64;
+    return TGSF_OK;
+}
+
+uint64_t tgsf_launch_count(const tgsf_ctx *c) { return c ? c->launches : 0; }
+
+int tgsf_prepass(int device, const uint8_t *ends5p, const uint8_t *ends3p, uint32_t n, uint32_t row_len,
+                 const uint8_t *const *lib_seq, const int32_t *lib_len, int32_t n_lib, float min_sim,
+                 int32_t *bases_num5p, int32_t *bases_num3p, int64_t *map5p, int64_t *map3p) {
+    if (!ends5p || !ends3p || !bases_num5p || !bases_num3p || row_len == 0 || row_len > 8192) {
+        set_err("prepass: bad arguments");
+        return TGSF_ERR_INVALID;
+    }
+    if (lib_seq && (n_lib <= 0 || n_lib > 1024 || !lib_len || !map5p || !map3p)) { set_err("prepass: bad library"); return TGSF_ERR_INVALID; }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    DBuf d_rows, d_cnt, d_maps;
+    AdapterSet ads;
+    Scratch scratch;
+    auto cleanup = [&]() { d_rows.release(); d_cnt.release(); d_maps.release(); ads.release(); scratch.buf.release(); };
+    const size_t row_bytes = (size_t)n * row_len;
+    int rc = d_rows.ensure(2 * row_bytes + 64);
+    if (rc == TGSF_OK) rc = d_cnt.ensure((size_t)2 * row_len * 4 * sizeof(int));
+    if (rc != TGSF_OK) { cleanup(); return rc; }
+    uint8_t *r5 = d_rows.as<uint8_t>(), *r3 = r5 + row_bytes;
+    cudaError_t e = cudaSuccess;
+    if (row_bytes) {
+        e = cudaMemcpy(r5, ends5p, row_bytes, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(r3, ends3p, row_bytes, cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemset(d_cnt.p, 0, (size_t)2 * row_len * 4 * sizeof(int));
+    if (e != cudaSuccess) { set_err("prepass upload: %s", cudaGetErrorString(e)); cleanup(); return TGSF_ERR_CUDA; }
+    int *c5 = d_cnt.as<int>(), *c3 = c5 + (size_t)row_len * 4;
+    if (n) {
+        const int grid = std::min<u32>((u32)sms * 4, cdiv(n, PRE_THREADS / 32));
+        k_base_content<<<grid, PRE_THREADS, (size_t)row_len * 4 * sizeof(u32)>>>(r5, n, row_len, c5);
+        k_base_content<<<grid, PRE_THREADS, (size_t)row_len * 4 * sizeof(u32)>>>(r3, n, row_len, c3);
+    }
+    if (lib_seq) {
+        rc = ads.build(lib_seq, lib_len, n_lib);
+        if (rc == TGSF_OK) {
+            if (min_sim < 0.9) min_sim = 0.9; // T.cpp:1151-1154 (float compared against a double literal)
+            for (auto &A : ads.host) {
+                if (A.qlen <= 0 || A.qlen > TGSF_MAX_ADAPTER_LEN) { rc = TGSF_ERR_INVALID; set_err("library adapter length"); break; }
+                int minK = static_cast<int>((1 - min_sim) * A.qlen) + 1; // T.cpp:1161
+                A.k_end = std::min(minK, A.qlen - 1);
+            }
+        }
+        if (rc == TGSF_OK) rc = ads.upload();
+        if (rc == TGSF_OK) rc = d_maps.ensure((size_t)2 * n_lib * sizeof(long long));
+        const u64 threads = (u64)sms * 4 * RES_THREADS;
+        if (rc == TGSF_OK) rc = scratch.ensure(threads, ads.max_cols, ads.max_nw);
+        if (rc != TGSF_OK) { cleanup(); return rc; }
+        cudaMemset(d_maps.p, 0, (size_t)2 * n_lib * sizeof(long long));
+        long long *m5 = d_maps.as<long long>(), *m3 = m5 + n_lib;
+        const AdapterCtx AC = ads.ctx();
+        for (int a = 0; a < n_lib && n; ++a) {
+            rc = for_nw(ads.host[(size_t)a].nw, [&](auto nwc) {
+                constexpr int NW = decltype(nwc)::value;
+                k_lib_search<NW><<<sms * 4, RES_THREADS>>>(r5, n, row_len, AC, a, m5 + a, scratch.buf.as<u64>(), scratch.stride);
+                k_lib_search<NW><<<sms * 4, RES_THREADS>>>(r3, n, row_len, AC, a, m3 + a, scratch.buf.as<u64>(), scratch.stride);
+                return check_launch("k_lib_search");
+            });
+            if (rc != TGSF_OK) { cleanup(); return rc; }
+        }
+        e = cudaMemcpy(map5p, m5, (size_t)n_lib * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess) e = cudaMemcpy(map3p, m3, (size_t)n_lib * sizeof(long long), cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { set_err("prepass maps: %s", cudaGetErrorString(e)); cleanup(); return TGSF_ERR_CUDA; }
+    }
+    e = cudaMemcpy(bases_num5p, c5, (size_t)row_len * 4 * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(bases_num3p, c3, (size_t)row_len * 4 * sizeof(int), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) { set_err("prepass download: %s", cudaGetErrorString(e)); return TGSF_ERR_CUDA; }
+    return TGSF_OK;
+}
+
+int tgsf_align_hw(int device, const uint8_t *queries, const uint32_t *q_off, const uint8_t *targets,
+                  const uint32_t *t_off, const int32_t *k, uint32_t n, tgsf_align_result *out) {
+    if (!q_off || !t_off || !k || !out) { set_err("align: NULL argument"); return TGSF_ERR_INVALID; }
+    if (n == 0) return TGSF_OK;
+    if (n > (1u << 20)) { set_err("align: at most 2^20 pairs per call"); return TGSF_ERR_INVALID; }
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int sms = prop.multiProcessorCount;
+    std::vector<const uint8_t *> seqs(n);
+    std::vector<int32_t> lens(n);
+    for (u32 i = 0; i < n; ++i) {
+        seqs[i] = queries + q_off[i];
+        lens[i] = (int32_t)(q_off[i + 1] - q_off[i]);
+        if (lens[i] > TGSF_MAX_ADAPTER_LEN) { set_err("align: query %u longer than %d", i, TGSF_MAX_ADAPTER_LEN); return TGSF_ERR_INVALID; }
+    }
+    AdapterSet ads;
+    DBuf d_t, d_toff, d_k, d_out;
+    Scratch scratch;
+    auto cleanup = [&]() { ads.release(); d_t.release(); d_toff.release(); d_k.release(); d_out.release(); scratch.buf.release(); };
+    int rc = ads.build(seqs.data(), lens.data(), (int)n);
+    if (rc == TGSF_OK) {
+        for (u32 i = 0; i < n; ++i)
+            if (lens[i] == 0 || t_off[i + 1] == t_off[i]) ads.host[i].nw = 0; // handled on the host below
+        rc = ads.upload();
+    }
+    const size_t tbytes = t_off[n];
+    if (rc == TGSF_OK) rc = d_t.ensure(tbytes + 64);
+    if (rc == TGSF_OK) rc = d_toff.ensure(((size_t)n + 1) * sizeof(u32));
+    if (rc == TGSF_OK) rc = d_k.ensure((size_t)n * sizeof(int));
+    if (rc == TGSF_OK) rc = d_out.ensure((size_t)n * sizeof(tgsf_align_result));
+    const u64 threads = (u64)sms * 2 * RES_THREADS;
+    if (rc == TGSF_OK) rc = scratch.ensure(threads, ads.max_cols, ads.max_nw);
+    if (rc != TGSF_OK) { cleanup(); return rc; }
+    cudaError_t e = cudaSuccess;
+    if (tbytes) e = cudaMemcpy(d_t.p, targets, tbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_toff.p, t_off, ((size_t)n + 1) * sizeof(u32), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_k.p, k, (size_t)n * sizeof(int), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemset(d_out.p, 0, (size_t)n * sizeof(tgsf_align_result));
+    if (e != cudaSuccess) { set_err("align upload: %s", cudaGetErrorString(e)); cleanup(); return TGSF_ERR_CUDA; }
+    const AdapterCtx AC = ads.ctx();
+    for (int nw = 1; nw <= 4; ++nw) {
+        bool any = false;
+        for (u32 i = 0; i < n; ++i) any |= ads.host[i].nw == nw;
+        if (!any) continue;
+        rc = for_nw(nw, [&](auto nwc) {
+            constexpr int NW = decltype(nwc)::value;
+            k_align_pairs<NW><<<sms * 2, RES_THREADS>>>(d_t.as<uint8_t>(), d_toff.as<u32>(), d_k.as<int>(), AC, n, NW,
+                                                        d_out.as<tgsf_align_result>(), scratch.buf.as<u64>(), scratch.stride);
+            return check_launch("k_align_pairs");
+        });
+        if (rc != TGSF_OK) { cleanup(); return rc; }
+    }
+    e = cudaMemcpy(out, d_out.p, (size_t)n * sizeof(tgsf_align_result), cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) { set_err("align download: %s", cudaGetErrorString(e)); return TGSF_ERR_CUDA; }
+    for (u32 i = 0; i < n; ++i) {
+        if (lens[i] == 0 || t_off[i + 1] == t_off[i]) { // E.cpp:161-179
+            tgsf_align_result R;
+            memset(&R, 0, sizeof(R));
+            R.edit_distance = lens[i];
+            R.n_locations = 1;
+            R.first_end = R.last_end = -1;
+            u32 h = 2166136261u;
+            const u32 v[2] = {0u, (u32)-1};
+            for (int w = 0; w < 2; ++w)
+                for (int b = 0; b < 4; ++b) { h ^= (v[w] >> (8 * b)) & 0xffu; h *= 16777619u; }
+            R.loc_hash = h;
+            out[i] = R;
+        }
+    }
+    return TGSF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,133 @@
+// Plumbing kernels: segment / tile / chunk tables and the exclusive scan they are built with.
+#pragma once
+#include "common.cuh"
+
+#define UTIL_THREADS 256
+#define SCANB_ITEMS 8
+#define SCANB_TILE (UTIL_THREADS * SCANB_ITEMS)
+
+// Block-level exclusive scan of in[0..n) into out[0..n); block totals into sums[blockIdx].
+__global__ void __launch_bounds__(UTIL_THREADS)
+k_scan_block(const u32 *__restrict__ in, u32 *__restrict__ out, u32 n, u32 *__restrict__ sums) {
+    __shared__ u32 warp_tot[UTIL_THREADS / 32];
+    const u32 base = blockIdx.x * SCANB_TILE + threadIdx.x * SCANB_ITEMS;
+    u32 v[SCANB_ITEMS];
+    u32 tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCANB_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        tsum += v[i];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < UTIL_THREADS / 32 ? warp_tot[lane] : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        if (lane < UTIL_THREADS / 32) warp_tot[lane] = w; // inclusive
+    }
+    __syncthreads();
+    u32 excl = inc - tsum + (warp ? warp_tot[warp - 1] : 0u);
+#pragma unroll
+    for (int i = 0; i < SCANB_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = excl;
+        excl += v[i];
+    }
+    if (threadIdx.x == UTIL_THREADS - 1) sums[blockIdx.x] = excl;
+}
+
+// out[i] += sums_scanned[block]; also writes the grand total to out[n].
+__global__ void __launch_bounds__(UTIL_THREADS)
+k_scan_add(u32 *__restrict__ out, u32 n, const u32 *__restrict__ sums_scanned,
+           const u32 *__restrict__ total) {
+    const u32 i = blockIdx.x * UTIL_THREADS + threadIdx.x;
+    if (i < n) out[i] += sums_scanned[i / SCANB_TILE];
+    if (i == 0) out[n] = *total;
+}
+
+// Raw pass segments = reads.  Also validates the read length against the bin capacity.
+__global__ void k_read_segments(DevBatch B, u64 *__restrict__ seg_start, int *__restrict__ seg_len,
+                                u64 *__restrict__ seg_sum, u32 *__restrict__ n_tiles, u32 max_bins,
+                                u32 *__restrict__ dev_status) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) return;
+    const u64 s = B.offsets[r];
+    const u64 len = B.offsets[r + 1] - s;
+    if (len / SCAN_BIN + 1 > (u64)max_bins || len > 0x7fffffffull) {
+        *dev_status = DEV_STATUS_BIN_OVERFLOW;
+        seg_len[r] = 0;
+        n_tiles[r] = 0;
+        seg_start[r] = s;
+        seg_sum[r] = 0;
+        return;
+    }
+    seg_start[r] = s;
+    seg_len[r] = (int)len;
+    seg_sum[r] = 0;
+    n_tiles[r] = (u32)((len + SCAN_TILE - 1) / SCAN_TILE);
+}
+
+__global__ void k_fill_tiles(const u32 *__restrict__ tile_off, u32 n_seg, TileEntry *__restrict__ tiles) {
+    const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_seg) return;
+    const u32 b = tile_off[s], e = tile_off[s + 1];
+    for (u32 t = b; t < e; ++t) {
+        TileEntry te;
+        te.seg = s;
+        te.tile = t - b;
+        tiles[t] = te;
+    }
+}
+
+// Number of absolute MID_CHUNK blocks overlapping the middle window of each active read
+// (0 when the window is shorter than the shortest adapter: tsmLen >= qLen, T.cpp:1237).
+__global__ void k_count_chunks(DevBatch B, const int *__restrict__ read_active, int end_len,
+                               int min_qlen, u32 *__restrict__ chunk_cnt, u32 *__restrict__ best_mid,
+                               u32 *__restrict__ mid_n, int n_adapters) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) return;
+    for (int a = 0; a < n_adapters; ++a) {
+        best_mid[(u64)r * n_adapters + a] = 0xffffffffu;
+        mid_n[(u64)r * n_adapters + a] = 0;
+    }
+    u32 c = 0;
+    if (read_active[r]) {
+        const u64 rs = B.offsets[r], re = B.offsets[r + 1];
+        const i64 tsm = (i64)(re - rs) - 2 * (i64)end_len;
+        if (tsm >= (i64)min_qlen && tsm > 0) {
+            const u64 mb = rs + (u64)end_len, me = re - (u64)end_len;
+            c = (u32)((me - 1) / MID_CHUNK - mb / MID_CHUNK + 1);
+        }
+    }
+    chunk_cnt[r] = c;
+}
+
+__global__ void k_fill_chunks(DevBatch B, const u32 *__restrict__ chunk_off, int end_len,
+                              ChunkEntry *__restrict__ chunks) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B.n_reads) return;
+    const u32 b = chunk_off[r], e = chunk_off[r + 1];
+    if (b == e) return;
+    const u32 first = (u32)((B.offsets[r] + (u64)end_len) / MID_CHUNK);
+    for (u32 t = b; t < e; ++t) {
+        ChunkEntry ce;
+        ce.read = r;
+        ce.chunk = first + (t - b);
+        chunks[t] = ce;
+    }
+}
+
+__global__ void k_check_pool(const u32 *__restrict__ pool_total, u32 pool_cap,
+                             u32 *__restrict__ dev_status) {
+    if (*pool_total > pool_cap) *dev_status = DEV_STATUS_POOL_OVERFLOW;
+}
