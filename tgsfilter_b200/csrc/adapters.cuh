@@ -214,8 +214,16 @@ k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int extra_len, int n_ad
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_ends: 5' and 3' windows (T.cpp:1266-1321).  One thread per (read, adapter, side).
-// out: end_n [n_reads][n_adapters][2] location counts (0 if thresholds fail),
+// k_ends: 5' and 3' windows (T.cpp:1266-1321).  One thread per (read, side); all tasks of one side
+// are contiguous so a warp runs one side.  Every phase is a flat loop of nearly the same trip
+// count in all lanes (no per-location nested searches), so warps stay converged:
+//   1. forward HW scan: best distance d, number of end columns with that distance, first / last
+//   2. start of the first location (reversed-query SHW) and its traceback -> mlen thresholds
+//   3. 3' only: HW scan of the REVERSED query from the right end of the window; the left-most
+//      column scoring d is min_i startLocations[i] (a column s scores d in the reversed scan iff
+//      NW(query, window[s..e]) == d for some e, and every such e is one of the forward end
+//      locations), which is all the merge of the {start_i, tLen} regions needs.
+// out: end_n [n_reads][n_adapters][2] location counts (0 if the thresholds fail),
 //      end_pos[n_reads][n_adapters][2]: side 0 -> max te (region {0, te}), side 1 -> min ts.
 // ---------------------------------------------------------------------------------------------
 template <int NW>
@@ -223,13 +231,24 @@ __global__ void __launch_bounds__(RES_THREADS)
 k_ends(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
        const int *__restrict__ read_active, int *__restrict__ end_n, int *__restrict__ end_pos,
        u64 *scratch, u64 scratch_stride) {
+    extern __shared__ u64 s_tab[]; // hw | fw | rv | rvhw tables of adapter a
     const DevAdapter A = C.ad[a];
-    const AdapterTables T = adapter_tables(C, a);
+    {
+        const u64 *src = C.peq_pool + A.peq_off;
+        for (int i = threadIdx.x; i < 4 * 256 * NW; i += RES_THREADS) s_tab[i] = src[i];
+    }
+    __syncthreads();
+    AdapterTables T;
+    T.hw = s_tab;
+    T.fw = s_tab + 256 * NW;
+    T.rv = s_tab + 512 * NW;
+    T.qlen = A.qlen;
+    const u64 *rvhw = s_tab + 768 * NW;
     const u64 tid = (u64)blockIdx.x * RES_THREADS + threadIdx.x;
     const u64 total = (u64)B.n_reads * 2;
     for (u64 w = tid; w < total; w += (u64)gridDim.x * RES_THREADS) {
-        const u32 r = (u32)(w >> 1);
-        const int side = (int)(w & 1);
+        const int side = w >= B.n_reads ? 1 : 0;
+        const u32 r = (u32)(side ? w - B.n_reads : w);
         const u64 oidx = ((u64)r * n_adapters + a) * 2 + side;
         int n_loc = 0, pos = 0;
         if (read_active[r] && A.k_end > 0) {
@@ -240,28 +259,37 @@ k_ends(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
             if (checkLen >= 5) {
                 const u64 lo = side == 0 ? rs : rs + (u64)(tLen - checkLen);
                 const u64 hi = lo + (u64)checkLen;
-                const int d = hw_best<NW>(T, B.bases, lo, hi, A.k_end);
-                if (d != 0x7fffffff) {
-                    Myers<NW> s;
-                    myers_init_hw<NW>(s, T.qlen);
-                    bool ok = true;
-                    int best_pos = side == 0 ? 0 : 0x7fffffff;
-                    for (u64 p = lo; p < hi && ok; ++p) {
-                        myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(B.bases + p) * NW, 0);
-                        if (s.score != d) continue;
-                        u64 s0 = 0;
-                        if (n_loc == 0 || side == 1) s0 = shw_start<NW>(T, B.bases, lo, p, d);
-                        if (n_loc == 0) {
-                            const int alen = nw_traceback_len<NW>(T, B.bases, s0, p, scratch + tid,
-                                                                  scratch_stride);
-                            if (alen - d < A.thr_end) { ok = false; break; }
+                // phase 1
+                Myers<NW> s;
+                myers_init_hw<NW>(s, T.qlen);
+                int d = 0x7fffffff, cnt = 0;
+                u64 first = 0, last = 0;
+#pragma unroll 4
+                for (u64 p = lo; p < hi; ++p) {
+                    myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(B.bases + p) * NW, 0);
+                    if (s.score < d) { d = s.score; cnt = 1; first = p; last = p; }
+                    else if (s.score == d) { ++cnt; last = p; }
+                }
+                if (d <= A.k_end) {
+                    // phase 2
+                    const u64 s0 = shw_start<NW>(T, B.bases, lo, first, d);
+                    const int alen = nw_traceback_len<NW>(T, B.bases, s0, first, scratch + tid, scratch_stride);
+                    if (alen - d >= A.thr_end) {
+                        n_loc = cnt;
+                        if (side == 0) {
+                            pos = (int)(last - rs) + 1; // te of the last location, T.cpp:1286
+                        } else {
+                            // phase 3
+                            myers_init_hw<NW>(s, T.qlen);
+                            u64 leftmost = s0;
+#pragma unroll 4
+                            for (u64 p = hi; p-- > lo;) {
+                                myers_step<NW, 0, true>(s, rvhw + (u32)__ldg(B.bases + p) * NW, 0);
+                                if (s.score == d) leftmost = p;
+                            }
+                            pos = (int)(leftmost - rs); // min ts, T.cpp:1310
                         }
-                        ++n_loc;
-                        if (side == 0) best_pos = (int)(p - rs) + 1;                // te, T.cpp:1286
-                        else best_pos = min(best_pos, (int)(s0 - rs));              // ts, T.cpp:1310
                     }
-                    if (!ok) n_loc = 0;
-                    pos = best_pos;
                 }
             }
         }

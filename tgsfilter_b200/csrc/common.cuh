@@ -38,6 +38,7 @@ struct DevAdapter {
 //   [0]            hw : top-padded (W = 64*nw - qlen wildcard rows below bit W), HW scans
 //   [256*nw]       fw : forward query, unpadded, NW pass of the traceback
 //   [512*nw]       rv : reversed query, unpadded, SHW start search
+//   [768*nw]       rvhw : reversed query, top-padded, right-to-left HW scan (3' window starts)
 
 struct DevParams {
     int min_len, max_len;

@@ -113,7 +113,7 @@ struct AdapterSet {
             A.qlen = len[a];
             A.nw = (len[a] + 63) / 64;
             A.peq_off = (u32)words;
-            words += (size_t)3 * 256 * (size_t)std::max(A.nw, 1);
+            words += (size_t)4 * 256 * (size_t)std::max(A.nw, 1);
             if (A.qlen > 0) {
                 max_q = std::max(max_q, A.qlen);
                 min_q = std::min(min_q, A.qlen);
@@ -126,15 +126,19 @@ struct AdapterSet {
             const int q = A.qlen, nw = A.nw;
             if (q <= 0) continue;
             const int W = 64 * nw - q;
-            u64 *hw = peq.data() + A.peq_off, *fw = hw + 256 * nw, *rv = fw + 256 * nw;
+            u64 *hw = peq.data() + A.peq_off, *fw = hw + 256 * nw, *rv = fw + 256 * nw, *rvhw = rv + 256 * nw;
             for (int b = 0; b < 256; ++b)
-                for (int i = 0; i < W; ++i) hw[b * nw + (i >> 6)] |= 1ull << (i & 63); // wildcards
+                for (int i = 0; i < W; ++i) { // wildcards
+                    hw[b * nw + (i >> 6)] |= 1ull << (i & 63);
+                    rvhw[b * nw + (i >> 6)] |= 1ull << (i & 63);
+                }
             for (int i = 0; i < q; ++i) {
                 const int b = seq[a][i];
                 hw[b * nw + ((W + i) >> 6)] |= 1ull << ((W + i) & 63);
                 fw[b * nw + (i >> 6)] |= 1ull << (i & 63);
                 const int br = seq[a][q - 1 - i];
                 rv[br * nw + (i >> 6)] |= 1ull << (i & 63);
+                rvhw[br * nw + ((W + i) >> 6)] |= 1ull << ((W + i) & 63);
             }
         }
         TRY(d_peq.ensure(std::max<size_t>(words, 1) * sizeof(u64)));
@@ -457,7 +461,7 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                         s.scratch.buf.as<u64>(), s.scratch.stride);
                     c->launches++;
                 }
-                k_ends<NW><<<res_grid, RES_THREADS, 0, st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
+                k_ends<NW><<<res_grid, RES_THREADS, 4 * 256 * NW * sizeof(u64), st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
                                                             s.end_n.as<int>(), s.end_pos.as<int>(),
                                                             s.scratch.buf.as<u64>(), s.scratch.stride);
                 c->launches++;
