@@ -34,23 +34,68 @@ static __device__ __forceinline__ AdapterTables adapter_tables(const AdapterCtx 
 // ---------------------------------------------------------------------------------------------
 // k_mid_scan
 // ---------------------------------------------------------------------------------------------
-// chunk_min: [n_adapters][chunk_stride] u8 (255 = nothing <= 254 / window too short)
-// best_mid:  [n_reads][n_adapters] u32, pre-set to 0xffffffff
+// One thread per chunk of a read's middle window; the thread scans the chunk for AP adapters of the
+// same word count at once: one LDS (64*AP*NW bits) per column serves all of them and the
+// independent Myers chains interleave.  The bottom-row score is not kept per column: Ph/Mh top bits
+// go into 32-bit histories and are folded every 16 columns; the exact per-column minimum is only
+// evaluated for a group when score - popc(minus bits) could reach k (otherwise no column of the
+// group can score <= k, and scores > k are never reported).
+//
+// chunk_min : [n_adapters][chunk_stride] u8 (255 = nothing <= min(k,254) / window too short)
+// chunk_cnt / chunk_first : [n_adapters][chunk_stride], written only where chunk_min != 255:
+//             number of columns of the chunk scoring chunk_min and the first of them (offset from
+//             the start of the bases stream, low 48 bits; the chunk minimum sits in the top 16)
+// best_mid  : [n_reads][n_adapters] u32, pre-set to 0xffffffff
+struct MidScanArgs {
+    int a[2];            // adapter indices handled by this launch (a[1] unused when AP == 1)
+    int end_len;
+    int chunk_shift;     // log2(chunk length)
+    u32 chunk_stride;
+    int n_adapters;
+};
+
 template <int NW>
+static __device__ void mid_chunk_record(const u64 *__restrict__ tab, int tab_stride, int qlen,
+                                        const uint8_t *__restrict__ bases, u64 sb, u64 ob, u64 oe,
+                                        int d, u32 &cnt, u64 &first) {
+    Myers<NW> s;
+    myers_init_hw<NW>(s, qlen);
+    cnt = 0;
+    first = 0;
+    for (u64 p = sb; p < oe; ++p) {
+        myers_step<NW, 0, true>(s, tab + (u32)bases[p] * tab_stride, 0);
+        if (p >= ob && s.score == d) {
+            if (cnt == 0) first = p;
+            ++cnt;
+        }
+    }
+}
+
+template <int NW, int AP>
 __global__ void __launch_bounds__(MID_THREADS)
-k_mid_scan_dyn(DevBatch B, AdapterCtx C, int a, int end_len, const ChunkEntry *__restrict__ chunks,
-               const u32 *__restrict__ n_chunks_ptr, u32 chunk_stride,
-               uint8_t *__restrict__ chunk_min, u32 *__restrict__ best_mid, int n_adapters) {
+k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__restrict__ chunks,
+               const u32 *__restrict__ n_chunks_ptr, uint8_t *__restrict__ chunk_min,
+               u32 *__restrict__ chunk_cnt, u64 *__restrict__ chunk_first,
+               u32 *__restrict__ best_mid) {
     const u32 n_chunks = *n_chunks_ptr; // device-side total (chunk_off[n_reads])
-    extern __shared__ u64 s_peq[]; // [256][NW] top-padded table of adapter a
-    const DevAdapter A = C.ad[a];
-    {
-        const u64 *src = C.peq_pool + A.peq_off;
-        for (int i = threadIdx.x; i < 256 * NW; i += MID_THREADS) s_peq[i] = src[i];
+    extern __shared__ __align__(16) u64 s_peq[]; // [256][AP][NW] top-padded tables
+    DevAdapter A[AP];
+#pragma unroll
+    for (int x = 0; x < AP; ++x) {
+        A[x] = C.ad[M.a[x]];
+        const u64 *src = C.peq_pool + A[x].peq_off;
+        for (int i = threadIdx.x; i < 256 * NW; i += MID_THREADS)
+            s_peq[(i / NW) * (AP * NW) + x * NW + (i % NW)] = src[i];
     }
     __syncthreads();
-    const int q = A.qlen;
-    const int k = A.k_mid;
+    constexpr int TS = AP * NW; // table stride per byte value (in u64)
+    const u64 chunk_len = 1ull << M.chunk_shift;
+    int halo = 0, qmin = 0x7fffffff;
+#pragma unroll
+    for (int x = 0; x < AP; ++x) {
+        halo = max(halo, A[x].halo_mid);
+        qmin = min(qmin, A[x].qlen);
+    }
     const uint4 *__restrict__ b16 = (const uint4 *)B.bases;
 
     for (u32 ci = blockIdx.x * MID_THREADS + threadIdx.x; ci < n_chunks;
@@ -58,57 +103,94 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, int a, int end_len, const ChunkEntry *_
         const ChunkEntry ce = chunks[ci];
         const u64 rs = B.offsets[ce.read];
         const u64 re = B.offsets[ce.read + 1];
-        const i64 len = (i64)(re - rs);
-        uint8_t result = 255;
-        if (k > 0 && len - 2 * (i64)end_len >= (i64)q) { // tsmLen >= qLen, T.cpp:1237
-            const u64 mb = rs + (u64)end_len, me = re - (u64)end_len; // middle window
-            const u64 cb = (u64)ce.chunk * MID_CHUNK;
-            const u64 ob = max(cb, mb), oe = min(cb + MID_CHUNK, me);  // columns this chunk reports
-            u64 sb = ob > (u64)A.halo_mid ? ob - (u64)A.halo_mid : 0;  // restart point
-            if (sb < mb) sb = mb;
-            Myers<NW> s;
-            myers_init_hw<NW>(s, q);
-            int best = 0x7fffffff;
-            // [sb, ob): halo, state only.  [ob, oe): tracked.
+        const i64 tsm = (i64)(re - rs) - 2 * (i64)M.end_len;
+        const u64 mb = rs + (u64)M.end_len, me = re - (u64)M.end_len; // middle window
+        const u64 cb = (u64)ce.chunk << M.chunk_shift;
+        const u64 ob = max(cb, mb), oe = min(cb + chunk_len, me);     // columns this chunk reports
+        u64 sb = ob > (u64)halo ? ob - (u64)halo : 0;                   // restart point
+        if (sb < mb) sb = mb;
+
+        u64 Pv[AP][NW], Mv[AP][NW];
+        int score[AP], best[AP];
+        u32 hP[AP], hM[AP];
+        bool on[AP];
+#pragma unroll
+        for (int x = 0; x < AP; ++x) {
+            Myers<NW> s0;
+            myers_init_hw<NW>(s0, A[x].qlen);
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { Pv[x][w] = s0.Pv[w]; Mv[x][w] = s0.Mv[w]; }
+            score[x] = A[x].qlen;
+            best[x] = 0x7fffffff;
+            hP[x] = hM[x] = 0;
+            on[x] = A[x].k_mid > 0 && tsm >= (i64)A[x].qlen; // tsmLen >= qLen, T.cpp:1237
+        }
+        if (tsm >= (i64)qmin) {
             u64 p = sb;
-            // head: bytes up to the next 16-byte boundary (only the first chunk of a window)
+            // head: single bytes up to the next 16-byte boundary (first chunk of a window only)
             while (p < oe && (p & 15ull)) {
-                myers_step<NW, 0, true>(s, s_peq + (u32)B.bases[p] * NW, 0);
-                if (p >= ob) best = min(best, s.score);
+                const u64 *eq = s_peq + (u32)B.bases[p] * TS;
+#pragma unroll
+                for (int x = 0; x < AP; ++x) {
+                    myers_step_hist<NW>(Pv[x], Mv[x], eq + x * NW, hP[x], hM[x]);
+                    score[x] += (int)(hP[x] & 1u) - (int)(hM[x] & 1u);
+                    if (p >= ob) best[x] = min(best[x], score[x]);
+                }
                 ++p;
             }
-            // halo groups (whole 16-byte groups strictly before ob; ob is 16-aligned here)
-            for (; p + 16 <= ob; p += 16) {
-                const uint4 v = __ldg(b16 + (p >> 4));
-                const u32 wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    myers_step<NW, 0, true>(s, s_peq + byte * NW, 0);
-                }
-            }
-            // body groups
+            // whole 16-byte groups: halo groups end at ob (16-aligned whenever a halo exists)
             for (; p + 16 <= oe; p += 16) {
                 const uint4 v = __ldg(b16 + (p >> 4));
                 const u32 wd[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    myers_step<NW, 0, true>(s, s_peq + byte * NW, 0);
-                    best = min(best, s.score);
+                    const u64 *eq = s_peq + byte * TS;
+#pragma unroll
+                    for (int x = 0; x < AP; ++x) myers_step_hist<NW>(Pv[x], Mv[x], eq + x * NW, hP[x], hM[x]);
+                }
+                const bool tracked = p >= ob;
+#pragma unroll
+                for (int x = 0; x < AP; ++x) {
+                    const u32 plus = hP[x] & 0xffffu, minus = hM[x] & 0xffffu;
+                    if (tracked && score[x] - __popc(minus) <= min(A[x].k_mid, best[x] - 1)) {
+                        int sc = score[x];
+                        for (int j = 15; j >= 0; --j) { // oldest column first
+                            sc += (int)((plus >> j) & 1u) - (int)((minus >> j) & 1u);
+                            best[x] = min(best[x], sc);
+                        }
+                    }
+                    score[x] += __popc(plus) - __popc(minus);
                 }
             }
             // tail
             for (; p < oe; ++p) {
-                myers_step<NW, 0, true>(s, s_peq + (u32)B.bases[p] * NW, 0);
-                if (p >= ob) best = min(best, s.score);
-            }
-            if (best <= k) {
-                result = (uint8_t)min(best, 254);
-                atomicMin(best_mid + (u64)ce.read * n_adapters + a, (u32)best);
+                const u64 *eq = s_peq + (u32)B.bases[p] * TS;
+#pragma unroll
+                for (int x = 0; x < AP; ++x) {
+                    myers_step_hist<NW>(Pv[x], Mv[x], eq + x * NW, hP[x], hM[x]);
+                    score[x] += (int)(hP[x] & 1u) - (int)(hM[x] & 1u);
+                    if (p >= ob) best[x] = min(best[x], score[x]);
+                }
             }
         }
-        chunk_min[(u64)a * chunk_stride + ci] = result;
+#pragma unroll
+        for (int x = 0; x < AP; ++x) {
+            uint8_t result = 255;
+            const u64 slot = (u64)M.a[x] * M.chunk_stride + ci;
+            if (on[x] && best[x] <= A[x].k_mid) {
+                result = (uint8_t)min(best[x], 254);
+                atomicMin(best_mid + (u64)ce.read * M.n_adapters + M.a[x], (u32)best[x]);
+                // rare: this chunk holds a candidate; record how many columns reach the chunk
+                // minimum and the first of them so that k_mid_count never has to rescan.
+                u32 cnt;
+                u64 first;
+                mid_chunk_record<NW>(s_peq + x * NW, TS, A[x].qlen, B.bases, sb, ob, oe, best[x], cnt, first);
+                chunk_cnt[slot] = cnt;
+                chunk_first[slot] = first | ((u64)best[x] << 48);
+            }
+            chunk_min[slot] = result;
+        }
     }
 }
 
@@ -119,16 +201,16 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, int a, int end_len, const ChunkEntry *_
 // ---------------------------------------------------------------------------------------------
 template <int NW, typename F>
 static __device__ void mid_for_each_end(const DevBatch &B, const AdapterTables &T,
-                                        const DevAdapter &A, int a, int end_len, u32 r, int d,
-                                        const u32 *__restrict__ chunk_off,
-                                        const ChunkEntry *__restrict__ chunks, u32 n_chunks,
+                                        const DevAdapter &A, int a, int end_len, int chunk_shift,
+                                        u32 r, int d, const u32 *__restrict__ chunk_off,
+                                        const ChunkEntry *__restrict__ chunks, u32 chunk_stride,
                                         const uint8_t *__restrict__ chunk_min, F f) {
     const u64 rs = B.offsets[r], re = B.offsets[r + 1];
     const u64 mb = rs + (u64)end_len, me = re - (u64)end_len;
     for (u32 ci = chunk_off[r]; ci < chunk_off[r + 1]; ++ci) {
-        if (chunk_min[(u64)a * n_chunks + ci] != (uint8_t)min(d, 254)) continue;
-        const u64 cb = (u64)chunks[ci].chunk * MID_CHUNK;
-        const u64 ob = max(cb, mb), oe = min(cb + MID_CHUNK, me);
+        if (chunk_min[(u64)a * chunk_stride + ci] != (uint8_t)min(d, 254)) continue;
+        const u64 cb = (u64)chunks[ci].chunk << chunk_shift;
+        const u64 ob = max(cb, mb), oe = min(cb + (1ull << chunk_shift), me);
         u64 sb = ob > (u64)A.halo_mid ? ob - (u64)A.halo_mid : 0;
         if (sb < mb) sb = mb;
         Myers<NW> s;
@@ -142,13 +224,15 @@ static __device__ void mid_for_each_end(const DevBatch &B, const AdapterTables &
     }
 }
 
+// One thread per (read, adapter) whose best middle distance is <= k: number of locations (sum of
+// the per-chunk records), PATH step of the first location, thresholds (T.cpp:1241-1250).
 // mid_n: [n_reads][n_adapters] number of regions (0 if the thresholds fail)
 template <int NW>
 __global__ void __launch_bounds__(RES_THREADS)
 k_mid_count(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
-            const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off,
-            const ChunkEntry *__restrict__ chunks, u32 n_chunks,
-            const uint8_t *__restrict__ chunk_min, u32 *__restrict__ mid_n, u64 *scratch,
+            const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off, u32 chunk_stride,
+            const uint8_t *__restrict__ chunk_min, const u32 *__restrict__ chunk_cnt,
+            const u64 *__restrict__ chunk_first, u32 *__restrict__ mid_n, u64 *scratch,
             u64 scratch_stride) {
     const DevAdapter A = C.ad[a];
     const AdapterTables T = adapter_tables(C, a);
@@ -157,20 +241,24 @@ k_mid_count(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
         const u32 bd = best_mid[(u64)r * n_adapters + a];
         if (bd == 0xffffffffu) continue;
         const int d = (int)bd;
-        const u64 mb = B.offsets[r] + (u64)end_len;
+        const uint8_t tag = (uint8_t)min(d, 254);
         u32 count = 0;
-        bool ok = true;
-        mid_for_each_end<NW>(B, T, A, a, end_len, r, d, chunk_off, chunks, n_chunks, chunk_min,
-                             [&](u64 p) {
-                                 if (count == 0) {
-                                     const u64 s0 = shw_start<NW>(T, B.bases, mb, p, d);
-                                     const int alen = nw_traceback_len<NW>(T, B.bases, s0, p,
-                                                                           scratch + tid, scratch_stride);
-                                     if (alen - d < A.thr_mid) { ok = false; return false; }
-                                 }
-                                 ++count;
-                                 return true;
-                             });
+        u64 first = 0;
+        for (u32 ci = chunk_off[r]; ci < chunk_off[r + 1]; ++ci) {
+            const u64 slot = (u64)a * chunk_stride + ci;
+            if (chunk_min[slot] != tag) continue;
+            const u64 rec = chunk_first[slot]; // first column | chunk minimum << 48
+            if ((int)(rec >> 48) != d) continue;
+            if (count == 0) first = rec & ((1ull << 48) - 1);
+            count += chunk_cnt[slot];
+        }
+        const u64 mb = B.offsets[r] + (u64)end_len;
+        const u64 s0 = shw_start<NW>(T, B.bases, mb, first, d);
+        int ok = mlen_decision(T.qlen, (int)(first - s0 + 1), d, A.thr_mid);
+        if (ok < 0) {
+            const int alen = nw_traceback_len<NW>(T, B.bases, s0, first, scratch + tid, scratch_stride);
+            ok = (alen - d >= A.thr_mid) ? 1 : 0;
+        }
         mid_n[(u64)r * n_adapters + a] = ok ? count : 0u;
     }
 }
@@ -178,9 +266,9 @@ k_mid_count(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
 // pool: Region {ts, te} per location (T.cpp:1247-1258), at mid_off[r*A+a] .. + mid_n
 template <int NW>
 __global__ void __launch_bounds__(RES_THREADS)
-k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int extra_len, int n_adapters,
-           const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off,
-           const ChunkEntry *__restrict__ chunks, u32 n_chunks,
+k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int chunk_shift, int extra_len,
+           int n_adapters, const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off,
+           const ChunkEntry *__restrict__ chunks, u32 chunk_stride,
            const uint8_t *__restrict__ chunk_min, const u32 *__restrict__ mid_n,
            const u32 *__restrict__ mid_off, Region *__restrict__ pool,
            const u32 *__restrict__ dev_status) {
@@ -198,8 +286,8 @@ k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int extra_len, int n_ad
         const u64 mb = rs + (u64)end_len;
         Region *out = pool + mid_off[key];
         u32 i = 0;
-        mid_for_each_end<NW>(B, T, A, a, end_len, r, d, chunk_off, chunks, n_chunks, chunk_min,
-                             [&](u64 p) {
+        mid_for_each_end<NW>(B, T, A, a, end_len, chunk_shift, r, d, chunk_off, chunks, chunk_stride,
+                             chunk_min, [&](u64 p) {
                                  const u64 s0 = shw_start<NW>(T, B.bases, mb, p, d);
                                  int ts = (int)(s0 - rs) - extra_len;       // T.cpp:1248,1253
                                  int te = (int)(p - rs) + 1 + extra_len;    // T.cpp:1249,1254
@@ -273,8 +361,12 @@ k_ends(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
                 if (d <= A.k_end) {
                     // phase 2
                     const u64 s0 = shw_start<NW>(T, B.bases, lo, first, d);
-                    const int alen = nw_traceback_len<NW>(T, B.bases, s0, first, scratch + tid, scratch_stride);
-                    if (alen - d >= A.thr_end) {
+                    int ok = mlen_decision(T.qlen, (int)(first - s0 + 1), d, A.thr_end);
+                    if (ok < 0) {
+                        const int alen = nw_traceback_len<NW>(T, B.bases, s0, first, scratch + tid, scratch_stride);
+                        ok = (alen - d >= A.thr_end) ? 1 : 0;
+                    }
+                    if (ok) {
                         n_loc = cnt;
                         if (side == 0) {
                             pos = (int)(last - rs) + 1; // te of the last location, T.cpp:1286

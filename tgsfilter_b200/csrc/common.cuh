@@ -17,9 +17,11 @@ typedef unsigned int u32;
 #define SCAN_BIN 100
 #define SCAN_TILE_BINS 32
 #define SCAN_TILE (SCAN_BIN * SCAN_TILE_BINS) /* 3200 bases */
-// K3: the middle window is cut into 16-byte-aligned absolute chunks of MID_CHUNK columns; each
-// chunk is re-started MID halo columns early (exact for scores <= k).
-#define MID_CHUNK 1024
+// K3: the middle window is cut into 16-byte-aligned absolute chunks of 2^chunk_shift columns
+// (1024..4096, chosen per batch); each chunk is re-started a halo of q+k-1 columns early (exact
+// for scores <= k).
+#define MID_CHUNK_SHIFT_MIN 10
+#define MID_CHUNK_SHIFT_MAX 12
 
 // Per-adapter constants precomputed on the host (tgsf_create), replacing the float expressions of
 // GetEditDistance (T.cpp:1233, 1250, 1267, 1271, 1287).
@@ -59,14 +61,16 @@ struct DevBatch {
     u32 n_reads;
 };
 
-struct __align__(8) TileEntry {
-    u32 seg;  // read index (raw pass) or piece index (clean pass)
-    u32 tile; // tile index inside the segment
+struct __align__(16) TileEntry {
+    u64 start; // absolute byte offset of the tile's first base in the batch streams
+    u32 seg;   // read index (raw pass) or piece index (clean pass)
+    u32 tile;  // tile index inside the segment (high 20 bits) | valid bases in the tile (low 12)
 };
+#define TILE_N_BITS 12
 
 struct __align__(8) ChunkEntry {
     u32 read;
-    u32 chunk; // absolute chunk index: covers bytes [chunk*MID_CHUNK, (chunk+1)*MID_CHUNK)
+    u32 chunk; // absolute chunk index: covers bytes [chunk << chunk_shift, (chunk+1) << chunk_shift)
 };
 
 struct __align__(8) Region {

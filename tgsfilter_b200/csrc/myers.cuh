@@ -84,6 +84,58 @@ static __device__ __forceinline__ void myers_step(Myers<NW> &s, const u64 *__res
     }
 }
 
+// HW column for the hot scan loop: no score register; the horizontal delta of the query's bottom
+// row (bit 63 of the last word of Ph / Mh) is shifted into two 32-bit histories instead, which the
+// caller folds into the score once per 16 columns (exact: see k_mid_scan).
+template <int NW>
+static __device__ __forceinline__ void myers_step_hist(u64 (&sPv)[NW], u64 (&sMv)[NW],
+                                                       const u64 *__restrict__ eq, u32 &hP, u32 &hM) {
+    int hin = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        u64 Eq = eq[w];
+        const u64 Pv = sPv[w], Mv = sMv[w];
+        const u64 hinNeg = (hin < 0) ? 1ull : 0ull;
+        const u64 Xv = Eq | Mv;
+        if (w > 0) Eq |= hinNeg;
+        const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        u64 Ph = Mv | ~(Xh | Pv);
+        u64 Mh = Pv & Xh;
+        if (w == NW - 1) {
+            hP = __funnelshift_l((u32)(Ph >> 32), hP, 1);
+            hM = __funnelshift_l((u32)(Mh >> 32), hM, 1);
+        }
+        const int hout = (w == NW - 1) ? 0 : (int)(Ph >> 63) - (int)(Mh >> 63);
+        Ph <<= 1;
+        Mh <<= 1;
+        if (w > 0) {
+            Ph |= (hin > 0) ? 1ull : 0ull;
+            Mh |= hinNeg;
+        }
+        sPv[w] = Mh | ~(Xv | Ph);
+        sMv[w] = Ph & Xv;
+        hin = hout;
+    }
+}
+
+// Measured and rejected (round 1): moving the 64-bit add and the two 1-bit shifts onto the FMA pipe
+// with mad.wide.u32 (IMAD.WIDE) made k_mid_scan 21 % slower (12.0 -> 14.6 ms on config[1]): ALU-pipe
+// instructions fell from 20.2 to 17.5 per column but IMAD.WIDE.U32 issues at about a quarter of the
+// IMAD rate, so the FMA pipe became the limiter.  The plain C form below already compiles to the
+// 32-bit IADD3 + IMAD.X pairs that split each add/shift one ALU op + one FMA op.
+
+// Bounds on the match count of ANY optimal global alignment of a q-long query against a tl-long
+// target with edit distance d: with X mismatches, I insertions, D deletions and M matches,
+// q = M+X+I, tl = M+X+D, d = X+I+D  =>  X + 2I = d - (tl - q) =: c  and  M = q - X - I is in
+// [q - c, q - ceil(c/2)].  Lets the resolve kernels skip the traceback whenever the threshold is
+// outside that interval (SURVEY.md §7 "Hard parts").
+static __device__ __forceinline__ int mlen_decision(int q, int tl, int d, int thr) {
+    const int c = d - (tl - q);
+    if (q - ((c + 1) >> 1) < thr) return 0;  // cannot reach the threshold
+    if (q - c >= thr) return 1;              // always reaches it
+    return -1;                               // traceback decides
+}
+
 // ---------------------------------------------------------------------------------------------
 // Small-window helpers used by the resolve kernels (one thread per window; byte loads).
 // ---------------------------------------------------------------------------------------------

@@ -96,15 +96,14 @@ static __device__ __forceinline__ void scan_word(BinAcc &a, u32 bw, u32 qw) {
 }
 
 // bases/quals: whole batch streams (16-byte aligned, readable up to the next 16-byte boundary
-// past the last segment).  seg_start/seg_len: absolute byte offset and length of each segment
-// (reads in the raw pass, kept pieces in the clean pass; len 0 = skip).  seg_sum: += sum(q - qtype).
+// past the last segment).  tiles: self-contained records (reads in the raw pass, kept pieces in
+// the clean pass).  seg_sum[seg] += sum(q - qtype).
 template <bool HAS_QUAL>
 __global__ void __launch_bounds__(SCAN_THREADS, 1)
 k_scan_tiles_dyn(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ quals,
-             const TileEntry *__restrict__ tiles, const u32 *__restrict__ n_tiles_ptr,
-             const u64 *__restrict__ seg_start,
-             const int *__restrict__ seg_len, u64 *__restrict__ seg_sum, u64 *__restrict__ bin_cnt,
-             u64 *__restrict__ bin_qual, int qtype, u32 max_bins, u32 *__restrict__ dev_status) {
+                 const TileEntry *__restrict__ tiles, const u32 *__restrict__ n_tiles_ptr,
+                 u64 *__restrict__ seg_sum, u64 *__restrict__ bin_cnt, u64 *__restrict__ bin_qual,
+                 int qtype, u32 max_bins, u32 *__restrict__ dev_status) {
     extern __shared__ __align__(128) uint8_t smem[];
     const u32 n_tiles = *n_tiles_ptr; // device-side total (tile_off[n_seg])
     uint8_t *stage_base = smem;
@@ -121,12 +120,23 @@ k_scan_tiles_dyn(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ 
     const u32 gwarp = blockIdx.x * SCAN_WARPS + warp;
     uint8_t *wbuf = stage_base + (size_t)warp * SCAN_STAGES * 2 * SCAN_BUF;
     u64 *wbar = bars + warp * SCAN_STAGES;
+    const uint4 *__restrict__ tile4 = (const uint4 *)tiles;
 
-    // issue the two bulk copies of tile t into stage st (lane 0 only)
-    auto issue = [&](u32 t, int st) {
-        const TileEntry te = tiles[t];
-        const u64 a0 = seg_start[te.seg] + (u64)te.tile * SCAN_TILE;
-        const int n = min(seg_len[te.seg] - (int)(te.tile * SCAN_TILE), SCAN_TILE);
+    auto load_entry = [&](u32 t) -> TileEntry {
+        TileEntry te;
+        te.start = 0; te.seg = 0; te.tile = 0;
+        if (t < n_tiles) {
+            const uint4 v = __ldg(tile4 + t);
+            te.start = ((u64)v.y << 32) | v.x;
+            te.seg = v.z;
+            te.tile = v.w;
+        }
+        return te;
+    };
+    // issue the two bulk copies of a tile into stage st (lane 0 only)
+    auto issue = [&](const TileEntry &te, int st) {
+        const u64 a0 = te.start;
+        const int n = (int)(te.tile & ((1u << TILE_N_BITS) - 1u));
         const u64 al = a0 & ~15ull;
         const u32 bytes = (u32)(((a0 - al) + (u64)n + 15ull) & ~15ull);
         const u32 bar = smem_u32(&wbar[st]);
@@ -139,13 +149,16 @@ k_scan_tiles_dyn(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ 
     u32 t = gwarp;
     int st = 0;
     u32 phase = 0;
-    if (t < n_tiles && lane == 0) issue(t, 0);
+    TileEntry cur = load_entry(t);
+    TileEntry nxt = load_entry(t + warps_total);
+    if (t < n_tiles && lane == 0) issue(cur, 0);
     for (; t < n_tiles; t += warps_total) {
-        const u32 tn = t + warps_total;
-        if (tn < n_tiles && lane == 0) issue(tn, st ^ 1);
-        const TileEntry te = tiles[t];
-        const u64 a0 = seg_start[te.seg] + (u64)te.tile * SCAN_TILE;
-        const int n = min(seg_len[te.seg] - (int)(te.tile * SCAN_TILE), SCAN_TILE);
+        if (t + warps_total < n_tiles && lane == 0) issue(nxt, st ^ 1);
+        const TileEntry nxt2 = load_entry(t + 2 * warps_total); // metadata two tiles ahead
+        const TileEntry te = cur;
+        const u64 a0 = te.start;
+        const int n = (int)(te.tile & ((1u << TILE_N_BITS) - 1u));
+        const u32 tile_idx = te.tile >> TILE_N_BITS;
         const u32 a = (u32)(a0 & 15ull);
         mbar_wait(smem_u32(&wbar[st]), phase);
 
@@ -195,7 +208,7 @@ k_scan_tiles_dyn(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ 
         cnt[4] = (u32)nvalid;
         qs[4] = acc.qall - qtype * nvalid;
         if (nvalid > 0) {
-            const u32 gb = te.tile * SCAN_TILE_BINS + lane;
+            const u32 gb = tile_idx * SCAN_TILE_BINS + lane;
             if (gb < SCAN_SMEM_BINS) {
                 u32 *p = sbins + gb * 10;
 #pragma unroll
@@ -220,6 +233,8 @@ k_scan_tiles_dyn(const uint8_t *__restrict__ bases, const uint8_t *__restrict__ 
         __syncwarp();
         st ^= 1;
         if (st == 0) phase ^= 1;
+        cur = nxt;
+        nxt = nxt2;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < SCAN_SMEM_BINS * 5; i += SCAN_THREADS) {

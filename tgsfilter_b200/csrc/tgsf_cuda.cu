@@ -196,7 +196,8 @@ struct Slot {
     bool has_qual = false;
     // work arrays
     DBuf seg_start, seg_len, seg_sum, seg_flag, tile_cnt, tile_off, tiles;
-    DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min;
+    DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first;
+    int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
     DBuf scan_tmp;
     Scratch scratch;
@@ -262,7 +263,7 @@ int slot_init(Slot &s) {
 void slot_release(Slot &s) {
     DBuf *bufs[] = {&s.in_bases, &s.in_quals, &s.in_offsets, &s.seg_start, &s.seg_len, &s.seg_sum,
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
-                    &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min,
+                    &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
                     &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.scratch.buf};
     for (DBuf *b : bufs) b->release();
@@ -283,7 +284,12 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     const int A = std::max(c->P.n_adapters, 1);
     if (s.pool_cap == 0) s.pool_cap = 65536;
     s.pieces_cap = n + s.pool_cap;
-    s.chunks_cap = (u32)(n_bases / MID_CHUNK + 2ull * n + 16);
+    // longer chunks amortise the halo; keep >= ~16 chunks per resident thread slot for balance
+    s.chunk_shift = MID_CHUNK_SHIFT_MIN;
+    while (s.chunk_shift < MID_CHUNK_SHIFT_MAX &&
+           (n_bases >> (s.chunk_shift + 1)) >= (u64)c->sm_count * 2048ull * 4ull)
+        s.chunk_shift++;
+    s.chunks_cap = (u32)((n_bases >> s.chunk_shift) + 2ull * n + 16);
     s.tiles_cap = (u32)(n_bases / SCAN_TILE + (u64)s.pieces_cap + 16);
     const size_t nseg = std::max<size_t>(n, s.pieces_cap) + 1;
     TRY(s.seg_start.ensure(nseg * sizeof(u64)));
@@ -300,6 +306,8 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.chunk_off.ensure(((size_t)n + 2) * sizeof(u32)));
     TRY(s.chunks.ensure((size_t)s.chunks_cap * sizeof(ChunkEntry)));
     TRY(s.chunk_min.ensure((size_t)s.chunks_cap * (size_t)A));
+    TRY(s.chunk_hits.ensure((size_t)s.chunks_cap * (size_t)A * sizeof(u32)));
+    TRY(s.chunk_first.ensure((size_t)s.chunks_cap * (size_t)A * sizeof(u64)));
     TRY(s.best_mid.ensure(((size_t)n * A + 1) * sizeof(u32)));
     TRY(s.mid_n.ensure(((size_t)n * A + 1) * sizeof(u32)));
     TRY(s.mid_off.ensure(((size_t)n * A + 2) * sizeof(u32)));
@@ -347,7 +355,7 @@ int launch_scan_pass(tgsf_ctx *c, Slot &s, u32 n_seg, u64 *bin_cnt, u64 *bin_qua
     const size_t scan_words = s.scan_tmp.cap / sizeof(u32);
     TRY(exclusive_scan(c, st, s.tile_cnt.as<u32>(), s.tile_off.as<u32>(), n_seg, s.scan_tmp.as<u32>(), scan_words));
     if (n_seg) {
-        k_fill_tiles<<<cdiv(n_seg, 256), 256, 0, st>>>(s.tile_off.as<u32>(), n_seg, s.tiles.as<TileEntry>());
+        k_fill_tiles<<<cdiv(n_seg, 256), 256, 0, st>>>(s.tile_off.as<u32>(), n_seg, s.seg_start.as<u64>(), s.seg_len.as<int>(), s.tiles.as<TileEntry>());
         c->launches++;
     }
     // the tile count lives on the device; the persistent grid reads it through tile_off[n_seg]
@@ -358,13 +366,11 @@ int launch_scan_pass(tgsf_ctx *c, Slot &s, u32 n_seg, u64 *bin_cnt, u64 *bin_qua
     if (s.has_qual) {
         k_scan_tiles_dyn<true><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(
             s.B.bases, s.B.quals, s.tiles.as<TileEntry>(), s.tile_off.as<u32>() + n_seg,
-            s.seg_start.as<u64>(), s.seg_len.as<int>(), s.seg_sum.as<u64>(), bin_cnt, bin_qual,
-            c->P.qtype, c->P.L.max_bins, status);
+            s.seg_sum.as<u64>(), bin_cnt, bin_qual, c->P.qtype, c->P.L.max_bins, status);
     } else {
         k_scan_tiles_dyn<false><<<grid, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(
             s.B.bases, s.B.quals, s.tiles.as<TileEntry>(), s.tile_off.as<u32>() + n_seg,
-            s.seg_start.as<u64>(), s.seg_len.as<int>(), s.seg_sum.as<u64>(), bin_cnt, bin_qual,
-            c->P.qtype, c->P.L.max_bins, status);
+            s.seg_sum.as<u64>(), bin_cnt, bin_qual, c->P.qtype, c->P.L.max_bins, status);
     }
     c->launches++;
     return check_launch("k_scan_tiles");
@@ -426,28 +432,45 @@ int launch_head(tgsf_ctx *c, Slot &s) {
 
     const bool filter = (P.flags & TGSF_FLAG_FILTER) != 0;
     if (filter && A > 0) {
-        k_count_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.read_active.as<int>(), P.end_len, c->ads.min_q,
+        k_count_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.read_active.as<int>(), P.end_len, s.chunk_shift, c->ads.min_q,
                                                      s.chunk_cnt.as<u32>(), s.best_mid.as<u32>(),
                                                      s.mid_n.as<u32>(), A);
         c->launches++;
         TRY(exclusive_scan(c, st, s.chunk_cnt.as<u32>(), s.chunk_off.as<u32>(), n, s.scan_tmp.as<u32>(),
                            s.scan_tmp.cap / sizeof(u32)));
-        k_fill_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.chunk_off.as<u32>(), P.end_len, s.chunks.as<ChunkEntry>());
+        k_fill_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.chunk_off.as<u32>(), P.end_len, s.chunk_shift, s.chunks.as<ChunkEntry>());
         c->launches++;
         const AdapterCtx AC = c->ads.ctx();
         const u32 *n_chunks_ptr = s.chunk_off.as<u32>() + n;
         const int res_grid = c->sm_count * 4;
-        for (int a = 0; a < A; ++a) {
-            const DevAdapter &Ah = c->ads.host[(size_t)a];
-            if (Ah.k_mid <= 0) continue;
-            TRY(for_nw(Ah.nw, [&](auto nwc) {
-                constexpr int NW = decltype(nwc)::value;
-                k_mid_scan_dyn<NW><<<c->sm_count * 8, MID_THREADS, 256 * NW * sizeof(u64), st>>>(
-                    s.B, AC, a, P.end_len, s.chunks.as<ChunkEntry>(), n_chunks_ptr, s.chunks_cap,
-                    s.chunk_min.as<uint8_t>(), s.best_mid.as<u32>(), A);
-                c->launches++;
-                return check_launch("k_mid_scan");
-            }));
+        // adapters with a live middle search, paired by word count: two per thread
+        for (int nw = 1; nw <= 4; ++nw) {
+            std::vector<int> grp;
+            for (int a = 0; a < A; ++a)
+                if (c->ads.host[(size_t)a].nw == nw && c->ads.host[(size_t)a].k_mid > 0) grp.push_back(a);
+            for (size_t i = 0; i < grp.size(); i += 2) {
+                const bool pair = i + 1 < grp.size();
+                MidScanArgs M;
+                M.a[0] = grp[i];
+                M.a[1] = pair ? grp[i + 1] : grp[i];
+                M.end_len = P.end_len;
+                M.chunk_shift = s.chunk_shift;
+                M.chunk_stride = s.chunks_cap;
+                M.n_adapters = A;
+                TRY(for_nw(nw, [&](auto nwc) {
+                    constexpr int NW = decltype(nwc)::value;
+                    if (pair)
+                        k_mid_scan_dyn<NW, 2><<<c->sm_count * 8, MID_THREADS, 256 * 2 * NW * sizeof(u64), st>>>(
+                            s.B, AC, M, s.chunks.as<ChunkEntry>(), n_chunks_ptr, s.chunk_min.as<uint8_t>(),
+                            s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(), s.best_mid.as<u32>());
+                    else
+                        k_mid_scan_dyn<NW, 1><<<c->sm_count * 8, MID_THREADS, 256 * NW * sizeof(u64), st>>>(
+                            s.B, AC, M, s.chunks.as<ChunkEntry>(), n_chunks_ptr, s.chunk_min.as<uint8_t>(),
+                            s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(), s.best_mid.as<u32>());
+                    c->launches++;
+                    return check_launch("k_mid_scan");
+                }));
+            }
         }
         CU(cudaEventRecord(s.ev_stage[3], st));
         for (int a = 0; a < A; ++a) {
@@ -456,9 +479,9 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                 constexpr int NW = decltype(nwc)::value;
                 if (Ah.k_mid > 0) {
                     k_mid_count<NW><<<res_grid, RES_THREADS, 0, st>>>(
-                        s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
-                        s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.mid_n.as<u32>(),
-                        s.scratch.buf.as<u64>(), s.scratch.stride);
+                        s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(), s.chunks_cap,
+                        s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
+                        s.mid_n.as<u32>(), s.scratch.buf.as<u64>(), s.scratch.stride);
                     c->launches++;
                 }
                 k_ends<NW><<<res_grid, RES_THREADS, 4 * 256 * NW * sizeof(u64), st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
@@ -504,7 +527,7 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
             TRY(for_nw(Ah.nw, [&](auto nwc) {
                 constexpr int NW = decltype(nwc)::value;
                 k_mid_emit<NW><<<res_grid, RES_THREADS, 0, st>>>(
-                    s.B, AC, a, P.end_len, P.extra_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
+                    s.B, AC, a, P.end_len, s.chunk_shift, P.extra_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
                     s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.mid_n.as<u32>(),
                     s.mid_off.as<u32>(), s.pool.as<Region>(), &H->status);
                 c->launches++;

@@ -77,23 +77,31 @@ __global__ void k_read_segments(DevBatch B, u64 *__restrict__ seg_start, int *__
     n_tiles[r] = (u32)((len + SCAN_TILE - 1) / SCAN_TILE);
 }
 
-__global__ void k_fill_tiles(const u32 *__restrict__ tile_off, u32 n_seg, TileEntry *__restrict__ tiles) {
+// Self-contained tile records (start, length, owner) so that the scan kernel needs exactly one
+// 16-byte load per tile, prefetched a tile ahead.
+__global__ void k_fill_tiles(const u32 *__restrict__ tile_off, u32 n_seg,
+                             const u64 *__restrict__ seg_start, const int *__restrict__ seg_len,
+                             TileEntry *__restrict__ tiles) {
     const u32 s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_seg) return;
     const u32 b = tile_off[s], e = tile_off[s + 1];
+    const u64 s0 = seg_start[s];
+    const int len = seg_len[s];
     for (u32 t = b; t < e; ++t) {
+        const u32 ti = t - b;
         TileEntry te;
+        te.start = s0 + (u64)ti * SCAN_TILE;
         te.seg = s;
-        te.tile = t - b;
+        te.tile = (ti << TILE_N_BITS) | (u32)min(len - (int)(ti * SCAN_TILE), SCAN_TILE);
         tiles[t] = te;
     }
 }
 
-// Number of absolute MID_CHUNK blocks overlapping the middle window of each active read
+// Number of absolute 2^chunk_shift blocks overlapping the middle window of each active read
 // (0 when the window is shorter than the shortest adapter: tsmLen >= qLen, T.cpp:1237).
 __global__ void k_count_chunks(DevBatch B, const int *__restrict__ read_active, int end_len,
-                               int min_qlen, u32 *__restrict__ chunk_cnt, u32 *__restrict__ best_mid,
-                               u32 *__restrict__ mid_n, int n_adapters) {
+                               int chunk_shift, int min_qlen, u32 *__restrict__ chunk_cnt,
+                               u32 *__restrict__ best_mid, u32 *__restrict__ mid_n, int n_adapters) {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B.n_reads) return;
     for (int a = 0; a < n_adapters; ++a) {
@@ -106,19 +114,19 @@ __global__ void k_count_chunks(DevBatch B, const int *__restrict__ read_active, 
         const i64 tsm = (i64)(re - rs) - 2 * (i64)end_len;
         if (tsm >= (i64)min_qlen && tsm > 0) {
             const u64 mb = rs + (u64)end_len, me = re - (u64)end_len;
-            c = (u32)((me - 1) / MID_CHUNK - mb / MID_CHUNK + 1);
+            c = (u32)(((me - 1) >> chunk_shift) - (mb >> chunk_shift) + 1);
         }
     }
     chunk_cnt[r] = c;
 }
 
 __global__ void k_fill_chunks(DevBatch B, const u32 *__restrict__ chunk_off, int end_len,
-                              ChunkEntry *__restrict__ chunks) {
+                              int chunk_shift, ChunkEntry *__restrict__ chunks) {
     const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= B.n_reads) return;
     const u32 b = chunk_off[r], e = chunk_off[r + 1];
     if (b == e) return;
-    const u32 first = (u32)((B.offsets[r] + (u64)end_len) / MID_CHUNK);
+    const u32 first = (u32)((B.offsets[r] + (u64)end_len) >> chunk_shift);
     for (u32 t = b; t < e; ++t) {
         ChunkEntry ce;
         ce.read = r;
