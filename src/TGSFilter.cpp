@@ -1,0 +1,662 @@
+// tgsfilter — drop-in CLI host over libtgsf_cuda (B200).
+//
+// Written from scratch against include/tgsf.h; mirrors the reference CLI's observable behaviour for
+// the filter / QC path: argv grammar, defaults and clamps of TGSFilter_cmd (T.cpp:198-503), the
+// pre-pass (GetFilterParameterTask, T.cpp:869-1216; parameter resolution in main, T.cpp:3058-3126),
+// FASTQ/FASTA records on stdout or -o (T.cpp:2020-2053) and the INFO: lines on stderr
+// (T.cpp:3071-3098, 3214-3235).  ("T.cpp" = reference src/TGSFilter.cpp.)
+//
+// The thread/queue runtime of the reference (1 reader + N workers + 1 writer, T.cpp:1808-1916) is
+// replaced by: parse -> pinned varlen batches -> tgsf_submit (async, two batches in flight per GPU,
+// batches dealt round-robin over the GPUs) -> tgsf_collect -> records in input order (= -t 1).
+//
+// Not in this host (SURVEY.md §8(f) "next"): BAM/SAM input (needs htslib), the HTML report, the
+// downsampling second pass.  They are rejected with a clear message, never silently skipped.
+#include <zlib.h>
+
+#include <algorithm>
+#include <cctype>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <iostream>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include <unistd.h>
+
+#include "../include/tgsf.h"
+#include "../include/tgsf_layout.h"
+
+using std::cerr;
+using std::endl;
+using std::string;
+
+namespace {
+
+// ---- parameters: Para_A24 (T.cpp:82-172) -------------------------------------------------------
+struct Params {
+    string InFile, OutFile, readType, AdapterFile;
+    int MinLen = 1000, MaxLen = 2147483647;
+    float MinQ = -1, MaxQ = 255;
+    int BCNum = 100000, BCLen = 150;
+    float EndBias = 1;
+    int HeadTrim = -1, TailTrim = -1;
+    bool ONLYAD = false;
+    int ADNum = 100000, EndLen = 150, EndMatchLen = 4, MidMatchLen = 35, ExtraLen = 50;
+    float EndSim = 0, MidSim = 0;
+    bool discard = false;
+    uint64_t GenomeSize = 0;
+    int DesiredDepth = 0, DesiredNum = 0;
+    float DesiredFrac = 0;
+    bool Downsample = false, Filter = true;
+    int Kmer = 11, MinRepeat = 0;
+    bool OnlyQC = false, FastaOut = false;
+    int n_thread = 16, Infq = 3, Outfq = 3;
+    bool OUTGZ = false;
+    int compLevel = 6;
+    int gpus = 1;                 // --gpus (extension; TGSF_GPUS env)
+    uint64_t batch_bases = 256ull << 20;
+};
+
+int usage() {
+    std::cout << "Usage: tgsfilter -i TGS.raw.fq.gz -x ont -o TGS.clean.fq.gz\n"
+                 " Input/Output options:\n"
+                 "   -i   <str>   input of fasta/fastq file\n"
+                 "   -x   <str>   read type (ont|clr|hifi)\n"
+                 "   -o   <str>   output of fasta/fastq file instead of stdout\n"
+                 " Basic filter options:\n"
+                 "   -l   <int>   min length of read to out [1000]\n"
+                 "   -L   <int>   max length of read to out\n"
+                 "   -q  <float>  min Phred average quality score\n"
+                 "   -Q  <float>  max Phred average quality score\n"
+                 "   -n   <int>   read number for base content check [100000]\n"
+                 "   -e   <int>   read end length for base content check [150]\n"
+                 "   -b  <float>  bias (%) of adjacent base content at read end [1]\n"
+                 "   -5   <int>   trim bases from the 5' end of the read\n"
+                 "   -3   <int>   trim bases from the 3' end of the read\n"
+                 " Adapter filter options:\n"
+                 "   -a   <str>   adapter sequence file \n"
+                 "   -A           disable reads filter, only for adapter identify\n"
+                 "   -N   <int>   read number for adapter identify [100000]\n"
+                 "   -E   <int>   read end length for adapter trim [150]\n"
+                 "   -m   <int>   min match length for end adapter [15]\n"
+                 "   -M   <int>   min match length for middle adapter [35]\n"
+                 "   -T   <int>   extra trim length for middle adpter on both side [50]\n"
+                 "   -s  <float>  min similarity for end adapter\n"
+                 "   -S  <float>  min similarity for middle adapter\n"
+                 "   -D           discard reads with middle adapter instead of split\n"
+                 " Downsampling options (-g -d -r -R -F): not available in this GPU host\n"
+                 "   -k   <int>   kmer size for repeat evaluations [11] \n"
+                 "   -p   <int>   min repeat length of reads [0] \n"
+                 " Other options:\n"
+                 "   --qc         disable all filter, only for quality control \n"
+                 "   -f           force FASTA output (discard quality) \n"
+                 "   -c   <int>   compression level (0-9) for compressed output [6]\n"
+                 "   -t   <int>   accepted for compatibility (the GPU replaces the worker threads)\n"
+                 "   --gpus <int> number of GPUs to shard batches over [1]\n"
+                 "   -h           show help [b200 host of v1.11]\n\n";
+    return 1;
+}
+
+uint64_t genome_size(const string &g) { // GetGenomeSize, T.cpp:178-196
+    if (g.empty()) return 0;
+    char u = (char)std::tolower((unsigned char)g.back());
+    double v = atof(g.c_str());
+    if (u == 'k') v *= 1e3;
+    else if (u == 'm') v *= 1e6;
+    else if (u == 'g') v *= 1e9;
+    return (uint64_t)v;
+}
+
+// TGSFilter_cmd, T.cpp:198-503: every '-' is removed from the flag token, so --qc == -qc.
+int parse_cmd(int argc, char **argv, Params *P) {
+    if (argc <= 2) { usage(); return 1; }
+    for (int i = 1; i < argc; i++) {
+        if (argv[i][0] != '-') { cerr << "Error: command option error! please check." << endl; return 1; }
+        string flag = argv[i];
+        flag.erase(std::remove(flag.begin(), flag.end(), '-'), flag.end());
+        auto need = [&]() -> bool {
+            if (i + 1 == argc) { cerr << "Error: Lack Argument for [ -" << flag << " ]" << endl; return false; }
+            i++;
+            return true;
+        };
+        if (flag == "i") { if (!need()) return 1; P->InFile = argv[i]; }
+        else if (flag == "o") { if (!need()) return 1; P->OutFile = argv[i]; }
+        else if (flag == "x") { if (!need()) return 1; P->readType = argv[i]; }
+        else if (flag == "l") { if (!need()) return 1; P->MinLen = atoi(argv[i]); if (P->MinLen < 100) P->MinLen = 100; }
+        else if (flag == "L") { if (!need()) return 1; P->MaxLen = atoi(argv[i]); }
+        else if (flag == "q") { if (!need()) return 1; P->MinQ = atof(argv[i]); }
+        else if (flag == "Q") { if (!need()) return 1; P->MaxQ = atof(argv[i]); }
+        else if (flag == "n") { if (!need()) return 1; P->BCNum = atoi(argv[i]); }
+        else if (flag == "e") { if (!need()) return 1; P->BCLen = atoi(argv[i]); }
+        else if (flag == "b") { if (!need()) return 1; P->EndBias = atof(argv[i]); }
+        else if (flag == "5") { if (!need()) return 1; P->HeadTrim = atoi(argv[i]); }
+        else if (flag == "3") { if (!need()) return 1; P->TailTrim = atoi(argv[i]); }
+        else if (flag == "a") { if (!need()) return 1; P->AdapterFile = argv[i]; }
+        else if (flag == "A") { P->ONLYAD = true; }
+        else if (flag == "N") { if (!need()) return 1; P->ADNum = atoi(argv[i]); }
+        else if (flag == "E") { if (!need()) return 1; P->EndLen = atoi(argv[i]); }
+        else if (flag == "m") { if (!need()) return 1; P->EndMatchLen = atoi(argv[i]); }
+        else if (flag == "M") { if (!need()) return 1; P->MidMatchLen = atoi(argv[i]); }
+        else if (flag == "T") { if (!need()) return 1; P->ExtraLen = atoi(argv[i]); }
+        else if (flag == "s") {
+            if (!need()) return 1;
+            P->EndSim = atof(argv[i]);
+            if (P->EndSim < 0.7) { P->EndSim = 0.7; cerr << "Warning: re set -s to : " << P->EndSim << endl; }
+        }
+        else if (flag == "S") {
+            if (!need()) return 1;
+            P->MidSim = atof(argv[i]);
+            if (P->MidSim < 0.8) { P->MidSim = 0.8; cerr << "Warning: reset -S to : " << P->MidSim << endl; }
+        }
+        else if (flag == "D") { P->discard = true; }
+        else if (flag == "g") { if (!need()) return 1; P->GenomeSize = genome_size(argv[i]); if (P->GenomeSize == 0) return 1; }
+        else if (flag == "d") { if (!need()) return 1; P->DesiredDepth = atoi(argv[i]); }
+        else if (flag == "r") { if (!need()) return 1; P->DesiredNum = atoi(argv[i]); }
+        else if (flag == "R") { if (!need()) return 1; P->DesiredFrac = atof(argv[i]); }
+        else if (flag == "k") { if (!need()) return 1; P->Kmer = atoi(argv[i]); }
+        else if (flag == "p") { if (!need()) return 1; P->MinRepeat = atoi(argv[i]); }
+        else if (flag == "F") { P->Filter = false; }
+        else if (flag == "qc") { P->OnlyQC = true; }
+        else if (flag == "c") { if (!need()) return 1; P->compLevel = atoi(argv[i]); }
+        else if (flag == "f") { P->FastaOut = true; }
+        else if (flag == "t") { if (!need()) return 1; P->n_thread = atoi(argv[i]); }
+        else if (flag == "gpus") { if (!need()) return 1; P->gpus = std::max(1, atoi(argv[i])); }
+        else if (flag == "help" || flag == "h") { usage(); return 1; }
+        else { cerr << "Error: UnKnow argument -" << flag << endl; return 1; }
+    }
+    if (P->InFile.empty()) { cerr << "Error: lack argument for the must: -i " << endl; exit(-1); }
+    if (access(P->InFile.c_str(), 0) != 0) { cerr << "Error: Can't find this file for -i " << P->InFile << endl; exit(-1); }
+    if (P->OnlyQC) P->Filter = false;
+    if (P->Filter) {
+        if (P->readType.empty()) { cerr << "Error: lack argument for the must: -x " << endl; exit(-1); }
+        const string rt = P->readType;
+        if (rt == "CLR" || rt == "clr") { cerr << "INFO: read type: PacBio continuous long read (clr)." << endl; P->readType = "clr"; }
+        else if (rt == "HIFI" || rt == "hifi" || rt == "CCS" || rt == "ccs") { cerr << "INFO: read type: PacBio highly accurate long reads (hifi)." << endl; P->readType = "hifi"; }
+        else if (rt == "ONT" || rt == "ont") { cerr << "INFO: read type: NanoPore reads (ont)." << endl; P->readType = "ont"; }
+        else { cerr << "Error: read type should be : clr/hifi/ccs/ont or CLR/HIFI/CCS/ONT." << endl; exit(-1); }
+        if (P->MidSim == 0) P->MidSim = P->readType == "hifi" ? 0.95 : 0.9;          // T.cpp:439-447
+        if (P->EndSim == 0) P->EndSim = P->readType == "hifi" ? 0.9 : P->readType == "clr" ? 0.8 : 0.75;
+        cerr << "INFO: min similarity for middle adapter: " << P->MidSim << endl;
+        cerr << "INFO: min similarity for end adapter: " << P->EndSim << endl;
+    }
+    if (P->DesiredNum > 0 || P->DesiredFrac > 0 || P->GenomeSize > 0 || P->DesiredDepth > 0) P->Downsample = true;
+    if (P->Downsample) {
+        cerr << "Error: downsampling (-g/-d/-r/-R) is not available in this GPU host; run the filter first." << endl;
+        exit(-1);
+    }
+    if (!P->Filter && !P->OnlyQC) {
+        cerr << "Error: Please set functional parameters for filter, downsampling or quality control." << endl;
+        exit(-1);
+    }
+    return 0;
+}
+
+string file_ext(const string &p) { size_t d = p.rfind('.'); return d == string::npos ? "" : p.substr(d + 1); }
+int file_type(const string &path) { // GetFileType, T.cpp:839-857
+    string ext = file_ext(path);
+    if (ext == "gz") ext = file_ext(path.substr(0, path.rfind('.')));
+    if (ext == "fa" || ext == "fasta") return 0;
+    if (ext == "fq" || ext == "fastq") return 1;
+    if (ext == "sam" || ext == "SAM" || ext == "bam" || ext == "BAM") return 2;
+    return 3;
+}
+
+char g_comp[256];
+string rev_comp(const string &s) { // rev_comp_seq, T.cpp:860-867
+    string r;
+    r.reserve(s.size());
+    for (int i = (int)s.size() - 1; i >= 0; --i) r += g_comp[(unsigned char)s[i]];
+    return r;
+}
+
+// ---- FASTA / FASTQ reader: 4-line FASTQ, 2-line FASTA, like FastxReader (T.cpp:521-782) ----------
+class FastxReader {
+public:
+    explicit FastxReader(const string &path) : isFastq_(file_type(path) == 1) {
+        f_ = gzopen(path.c_str(), "rb"); // transparent for plain files, multi-member aware
+        if (f_) gzbuffer(f_, 1 << 20);
+        buf_.resize(1 << 20);
+    }
+    ~FastxReader() { if (f_) gzclose(f_); }
+    bool ok() const { return f_ != nullptr; }
+    // false at end of input or on a malformed record (the reference stops there too)
+    bool read(string &name, string &seq, string &qual) {
+        if (!f_) return false;
+        if (isFastq_) {
+            string strand;
+            for (int i = 0; i < 5; i++) {
+                if (!line(name)) return false;
+                if (!name.empty() && name[0] == '@') {
+                    if (!line(seq) || !line(strand)) return false;
+                    if (!strand.empty() && strand[0] == '+' && !seq.empty()) break;
+                }
+            }
+            if (name.empty()) { cerr << "Error: input format wrong!" << endl; return false; }
+            name = name.substr(1);
+            if (!line(qual) || qual.empty()) { cerr << "Error: quality are empty:" << name << endl; return false; }
+            if (qual.size() != seq.size()) { cerr << "warning: sequence and quality have different length:" << name << endl; return false; }
+            return true;
+        }
+        for (int i = 0; i < 3; i++) {
+            if (!line(name)) return false;
+            if (!name.empty() && name[0] == '>') break;
+        }
+        if (name.empty()) { cerr << "Error: input format wrong!" << endl; return false; }
+        name = name.substr(1);
+        if (!line(seq) || seq.empty()) { cerr << "Error: sequence are empty:" << name << endl; return false; }
+        qual.clear();
+        return true;
+    }
+
+private:
+    bool fill() {
+        int n = gzread(f_, buf_.data(), (unsigned)buf_.size());
+        if (n <= 0) return false;
+        pos_ = 0;
+        len_ = (size_t)n;
+        return true;
+    }
+    bool line(string &out) {
+        out.clear();
+        while (true) {
+            if (pos_ == len_ && !fill()) return !out.empty();
+            const char *p = buf_.data() + pos_;
+            const char *nl = (const char *)memchr(p, '\n', len_ - pos_);
+            if (nl) {
+                out.append(p, nl - p);
+                pos_ += (size_t)(nl - p) + 1;
+                if (!out.empty() && out.back() == '\r') out.pop_back();
+                return true;
+            }
+            out.append(p, len_ - pos_);
+            pos_ = len_;
+        }
+    }
+    gzFile f_ = nullptr;
+    bool isFastq_;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
+};
+
+// ---- pinned varlen batch --------------------------------------------------------------------------
+struct Batch {
+    uint8_t *bases = nullptr, *quals = nullptr;
+    size_t cap = 0, used = 0;
+    std::vector<uint64_t> offsets{0};
+    std::vector<string> names;
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        size_t ncap = std::max(want, cap * 2 + (1 << 20));
+        uint8_t *nb = nullptr, *nq = nullptr;
+        if (tgsf_host_alloc((void **)&nb, ncap) != TGSF_OK || tgsf_host_alloc((void **)&nq, ncap) != TGSF_OK) return false;
+        if (used) { memcpy(nb, bases, used); memcpy(nq, quals, used); }
+        tgsf_host_free(bases);
+        tgsf_host_free(quals);
+        bases = nb; quals = nq; cap = ncap;
+        return true;
+    }
+    bool add(const string &name, const string &seq, const string &qual, bool has_qual) {
+        if (!reserve(used + seq.size() + 64)) return false;
+        memcpy(bases + used, seq.data(), seq.size());
+        if (has_qual) memcpy(quals + used, qual.data(), seq.size());
+        used += seq.size();
+        offsets.push_back(used);
+        names.push_back(name);
+        return true;
+    }
+    void clear() { used = 0; offsets.assign(1, 0); names.clear(); }
+    void release() { tgsf_host_free(bases); tgsf_host_free(quals); bases = quals = nullptr; cap = 0; }
+    uint32_t n() const { return (uint32_t)names.size(); }
+};
+
+string new_seq_name(const string &raw, int number) { // newSeqName, T.cpp:1680-1701
+    string add = ":" + std::to_string(number), out;
+    bool found = false;
+    for (char c : raw) {
+        if (std::isspace((unsigned char)c) && !found) { out += add; out += c; found = true; }
+        else out += c;
+    }
+    if (!found) out += add;
+    return out;
+}
+
+// one gzip member per record, like DeflateCompress (T.cpp:786-812): decompresses identically
+bool gz_member(const string &in, int level, string &out) {
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
+    out.resize(deflateBound(&zs, in.size()) + 32);
+    zs.next_in = (Bytef *)in.data();
+    zs.avail_in = (uInt)in.size();
+    zs.next_out = (Bytef *)&out[0];
+    zs.avail_out = (uInt)out.size();
+    int rc = deflate(&zs, Z_FINISH);
+    out.resize(zs.total_out);
+    deflateEnd(&zs);
+    return rc == Z_STREAM_END;
+}
+
+const char *kLib[TGSF_LIB_ADAPTERS] = { // adapterLib, T.cpp:2969-2991
+    "ATCTCTCTCTTTTCCTCCTCCTCCGTTGTTGTTGTTGAGAGAGAT", "ATCTCTCTCAACAACAACAACGGAGGAGGAGGAAAAGAGAGAGAT",
+    "AAAAAAAAAAAAAAAAAATTAACGGAGGAGGAGGA", "TCCTCCTCCTCCGTTAATTTTTTTTTTTTTTTTTT",
+    "AATGTACTTCGTTCAGTTACGTATTGCT", "AGCAATACGTAACTGAACGAAGTACATT",
+    "GCAATACGTAACTGAACGAAGT", "ACTTCGTTCAGTTACGTATTGC",
+    "GTTTTCGCATTTATCGTGAAACGCTTTCGCGTTTTTCGTGCGCCGCTTCA", "TGAAGCGGCGCACGAAAAACGCGAAAGCGTTTCACGATAAATGCGAAAAC",
+    "GGCGTCTGCTTGGGTGTTTAACCTTTTTGTCAGAGAGGTTCCAAGTCAGAGAGGTTCCT", "AGGAACCTCTCTGACTTGGAACCTCTCTGACAAAAAGGTTAAACACCCAAGCAGACGCC",
+    "GGAACCTCTCTGACTTGGAACCTCTCTGACAAAAAGGTTAAACACCCAAGCAGACGCCAGCAAT", "ATTGCTGGCGTCTGCTTGGGTGTTTAACCTTTTTGTCAGAGAGGTTCCAAGTCAGAGAGGTTCC",
+    "TTTTTTTTCCTGTACTTCGTTCAGTTACGTATTGCT", "AGCAATACGTAACTGAACGAAGTACAGGAAAAAAAA",
+    "GCAATACGTAACTGAACGAAGTACAGG", "CCTGTACTTCGTTCAGTTACGTATTGC",
+    "ACGTAACTGAACGAAGTACAGG", "CCTGTACTTCGTTCAGTTACGT",
+    "CTTGCGGGCGGCGGACTCTCCTCTGAAGATAGAGCGACAGGCAAG", "CTTGCCTGTCGCTCTATCTTCAGAGGAGAGTCCGCCGCCCGCAAG"};
+
+// decision loop of CheckBaseContent, T.cpp:1097-1134
+int base_content_trim(const std::vector<int32_t> &bn, int checkLen, int seqNum, float EndBias) {
+    int maxDiff = (seqNum * EndBias) / 100;
+    int trimLen = 0;
+    for (int i = 1; i < checkLen - 1; i++) {
+        bool leftFlag = false, rightFlag = false;
+        int l = std::min(i, 5), r = std::min(checkLen - i - 1, 5);
+        for (int j = 0; j < 4; j++) {
+            for (int x = 1; x <= l; x++)
+                if (abs(bn[i * 4 + j] - bn[(i - x) * 4 + j]) > maxDiff) { leftFlag = true; break; }
+            for (int x = 1; x <= r; x++)
+                if (abs(bn[(i + x) * 4 + j] - bn[i * 4 + j]) > maxDiff) { rightFlag = true; break; }
+        }
+        if (leftFlag && rightFlag) trimLen = i + 1;
+    }
+    return trimLen;
+}
+
+void die_tgsf(const char *what) {
+    cerr << "Error: " << what << ": " << tgsf_last_error() << endl;
+    exit(-1);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    Params P;
+    if (const char *e = getenv("TGSF_GPUS")) P.gpus = std::max(1, atoi(e));
+    if (parse_cmd(argc, argv, &P) == 1) return 1;
+    for (int i = 0; i < 256; i++) g_comp[i] = 'N';
+    const char *pairs[] = {"AT", "GC", "CG", "TA", "at", "gc", "cg", "ta", "MK", "RY", "WW", "SS", "YR", "KM",
+                           "mk", "ry", "ww", "ss", "yr", "km"};
+    for (const char *p : pairs) g_comp[(unsigned char)p[0]] = p[1];
+
+    P.Infq = file_type(P.InFile);
+    if (!P.OutFile.empty() && !P.OnlyQC) {
+        P.Outfq = file_type(P.OutFile);
+        if (file_ext(P.OutFile) == "gz") P.OUTGZ = true;
+    } else {
+        P.Outfq = P.FastaOut ? 0 : (P.Infq == 2 ? 1 : P.Infq);
+    }
+    if (P.Infq == 3 || P.Outfq == 3) {
+        cerr << "Error: The file name suffix should be '.[fastq|fq|fasta|fa][.gz] or .[sam|bam]'" << endl;
+        if (P.Infq == 3) cerr << "Error: Please check your input file name: " << P.InFile << endl;
+        else cerr << "Error: Please check your output file name: " << P.OutFile << endl;
+        return 1;
+    }
+    if (P.Infq == 2) { cerr << "Error: BAM/SAM input needs htslib, which this GPU host is not linked against." << endl; return 1; }
+    if (P.Infq == 0 && P.Outfq == 1) { cerr << "Error: Fasta format input file can't output fastq format file" << endl; return 1; }
+    const bool has_qual = P.Infq == 1;
+
+    // ---- pre-pass: read_fastx (T.cpp:949-982) + Get_qType (T.cpp:1042-1077) -----------------------
+    int checkLen = std::max(std::max(P.EndLen, P.BCLen), 100);
+    int minLen = std::max(P.MinLen, 2 * checkLen);
+    int maxSeq = std::max(P.ADNum, P.BCNum);
+    std::vector<uint8_t> e5, e3;
+    int seqNum = 0, minQ = 255, maxQ = 0;
+    {
+        FastxReader rd(P.InFile);
+        if (!rd.ok()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
+        string name, seq, qual;
+        while (rd.read(name, seq, qual)) {
+            int L = (int)seq.size();
+            if (L < minLen) continue;
+            if (seqNum >= maxSeq) break;
+            seqNum++;
+            e5.insert(e5.end(), seq.begin(), seq.begin() + checkLen);
+            string t = rev_comp(seq.substr(L - checkLen));
+            e3.insert(e3.end(), t.begin(), t.end());
+            for (int i = 0; i < checkLen && has_qual; i++) {
+                char q = qual[i];
+                if (minQ > q) minQ = q;
+                if (maxQ < q) maxQ = q;
+            }
+        }
+    }
+    int qType = 0;
+    if (has_qual) {
+        if (minQ >= 33 && minQ <= 78 && maxQ >= 33 && maxQ <= 127) qType = 33;
+        else if (minQ >= 64 && minQ <= 108 && maxQ >= 64 && maxQ <= 127) qType = 64;
+        else if (minQ < 55) qType = 33;
+        else qType = 64;
+        cerr << "INFO: base quality scoring: Phred" << qType << endl;
+        minQ -= qType;
+        maxQ -= qType;
+        if (P.MinQ >= 0) {
+            if (P.MinQ >= maxQ) {
+                cerr << "Warning: max base quality score was: " << maxQ << endl;
+                cerr << "INFO: Please reset -q parameter." << endl;
+                exit(-1);
+            }
+        } else {
+            if (maxQ > 10 && P.readType == "clr") P.MinQ = 10;
+            else if (maxQ > 20 && P.readType == "hifi") P.MinQ = 20;
+            else if (maxQ > 10 && P.readType == "ont") P.MinQ = 10;
+            else P.MinQ = 0;
+        }
+    }
+
+    std::vector<string> adapters; // the global `adapters` set (T.cpp:1324); order is irrelevant
+    auto add_adapter = [&](const string &a) { if (std::find(adapters.begin(), adapters.end(), a) == adapters.end()) adapters.push_back(a); };
+    if (P.Filter) {
+        std::vector<int32_t> bn5((size_t)checkLen * 4), bn3((size_t)checkLen * 4);
+        std::vector<int64_t> m5(TGSF_LIB_ADAPTERS, 0), m3(TGSF_LIB_ADAPTERS, 0);
+        std::vector<const uint8_t *> lib_seq;
+        std::vector<int32_t> lib_len;
+        for (const char *a : kLib) { lib_seq.push_back((const uint8_t *)a); lib_len.push_back((int32_t)strlen(a)); }
+        const bool search = P.AdapterFile.empty();
+        const uint8_t dummy = 0;
+        if (tgsf_prepass(0, seqNum ? e5.data() : &dummy, seqNum ? e3.data() : &dummy, (uint32_t)seqNum, (uint32_t)checkLen,
+                         search ? lib_seq.data() : nullptr, lib_len.data(), TGSF_LIB_ADAPTERS, P.MidSim, bn5.data(),
+                         bn3.data(), m5.data(), m3.data()) != TGSF_OK)
+            die_tgsf("tgsf_prepass");
+        if (P.HeadTrim < 0) P.HeadTrim = base_content_trim(bn5, checkLen, seqNum, P.EndBias);
+        if (P.TailTrim < 0) P.TailTrim = base_content_trim(bn3, checkLen, seqNum, P.EndBias);
+        cerr << "INFO: trim 5' end length: " << P.HeadTrim << endl;
+        cerr << "INFO: trim 3' end length: " << P.TailTrim << endl;
+        cerr << "INFO: min output reads length: " << P.MinLen << endl;
+        if (has_qual) cerr << "INFO: min Phred average quality score: " << P.MinQ << endl;
+        if (!search) { // Get_adapters, T.cpp:2923-2942
+            FastxReader ar(P.AdapterFile);
+            string name, seq, qual;
+            while (ar.read(name, seq, qual)) { add_adapter(seq); add_adapter(rev_comp(seq)); }
+            int num = 0;
+            for (const string &a : adapters) cerr << "INFO: input adapter " << ++num << " :" << a << endl;
+        } else { // tail of adapterSearch (T.cpp:1178-1208) + selection (T.cpp:3081-3125)
+            float minSim = P.MidSim;
+            if (minSim < 0.9) minSim = 0.9;
+            auto pick = [&](const std::vector<int64_t> &maps, string &ad, float &dep) {
+                int best = -1;
+                for (int i = 0; i < TGSF_LIB_ADAPTERS; i++)
+                    if (maps[i] > 0 && (best < 0 || maps[i] > maps[best])) best = i;
+                ad.clear();
+                dep = 0;
+                if (best >= 0) {
+                    float meanDep = static_cast<float>((int)maps[best]) / strlen(kLib[best]);
+                    if (meanDep >= 2 * minSim) { ad = kLib[best]; dep = meanDep; }
+                }
+            };
+            string a5, a3;
+            float d5, d3;
+            pick(m5, a5, d5);
+            pick(m3, a3, d3);
+            if (d5 > 5 * d3) { a3 = ""; d3 = 0; }
+            else if (d3 > 5 * d5) { a5 = ""; d5 = 0; }
+            cerr << "INFO: 5' adapter: " << a5 << endl;
+            cerr << "INFO: 3' adapter: " << a3 << endl;
+            cerr << "INFO: mean depth of 5' adapter: " << d5 << endl;
+            cerr << "INFO: mean depth of 3' adapter: " << d3 << endl;
+            if (P.ONLYAD) return 0;
+            if (!a5.empty()) { add_adapter(a5); add_adapter(rev_comp(a5)); }
+            if (!a3.empty()) { add_adapter(a3); add_adapter(rev_comp(a3)); }
+            if (a5.empty() && a3.empty()) {
+                if (P.readType == "hifi" || P.readType == "clr") {
+                    add_adapter(kLib[0]); add_adapter(kLib[1]);
+                    cerr << "INFO: set PacBio blunt adapter to trim: " << kLib[0] << endl;
+                } else if (P.readType == "ont") {
+                    add_adapter(kLib[8]); add_adapter(kLib[9]);
+                    cerr << "INFO: set NanoPore rapid adapter to trim: " << kLib[8] << endl;
+                }
+            }
+        }
+    }
+
+    // ---- contexts: one per GPU ---------------------------------------------------------------------
+    tgsf_params tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.min_len = P.MinLen; tp.max_len = P.MaxLen; tp.min_q = P.MinQ; tp.max_q = P.MaxQ;
+    tp.bc_len = P.BCLen; tp.head_trim = P.HeadTrim; tp.tail_trim = P.TailTrim;
+    tp.end_len = P.EndLen; tp.end_match_len = P.EndMatchLen; tp.mid_match_len = P.MidMatchLen;
+    tp.extra_len = P.ExtraLen; tp.end_sim = P.EndSim; tp.mid_sim = P.MidSim;
+    tp.kmer = P.Kmer; tp.min_repeat = P.MinRepeat; tp.qtype = qType;
+    tp.flags = (P.Filter ? TGSF_FLAG_FILTER : 0) | (P.OnlyQC ? TGSF_FLAG_ONLY_QC : 0) | (P.discard ? TGSF_FLAG_DISCARD_MID : 0);
+    std::vector<const uint8_t *> aseq;
+    std::vector<int32_t> alen;
+    for (const string &a : adapters) { aseq.push_back((const uint8_t *)a.data()); alen.push_back((int32_t)a.size()); }
+    tp.n_adapters = (int32_t)aseq.size();
+    tp.adapter_seq = aseq.data();
+    tp.adapter_len = alen.data();
+    tp.n_slots = 2;
+    std::vector<tgsf_ctx *> ctx((size_t)P.gpus, nullptr);
+    for (int g = 0; g < P.gpus; g++)
+        if (tgsf_create(g, &tp, &ctx[(size_t)g]) != TGSF_OK) die_tgsf("tgsf_create");
+
+    // ---- main pass -----------------------------------------------------------------------------------
+    FILE *out = stdout;
+    if (!P.OnlyQC && !P.OutFile.empty()) {
+        out = fopen(P.OutFile.c_str(), "wb");
+        if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
+    }
+    const int slots = 2 * P.gpus;
+    std::vector<Batch> ring((size_t)slots);
+    std::deque<int> inflight; // ring indices in submission order; batch i runs on GPU (i % gpus)
+    uint64_t rawNum = 0, rawBases = 0, cleanNum = 0, cleanBases = 0, submitted = 0;
+    std::vector<tgsf_read_result> rr;
+    std::vector<tgsf_piece> pc;
+
+    auto retire = [&]() {
+        const int bi = inflight.front();
+        inflight.pop_front();
+        Batch &b = ring[(size_t)bi];
+        tgsf_ctx *c = ctx[(size_t)(bi % P.gpus)];
+        rr.resize(b.n());
+        pc.resize((size_t)b.n() + 4096);
+        uint32_t np = 0;
+        int rc = tgsf_collect(c, rr.data(), b.n(), pc.data(), (uint32_t)pc.size(), &np);
+        if (rc == TGSF_ERR_CAPACITY && np > pc.size()) {
+            pc.resize(np);
+            rc = tgsf_collect(c, rr.data(), b.n(), pc.data(), (uint32_t)pc.size(), &np);
+        }
+        if (rc != TGSF_OK) die_tgsf("tgsf_collect");
+        uint32_t last = UINT32_MAX;
+        int pass = 1;
+        string rec, gz;
+        for (uint32_t i = 0; i < np; i++) { // T.cpp:1976-2059
+            const tgsf_piece &p = pc[i];
+            if ((uint32_t)p.read != last) { last = (uint32_t)p.read; pass = 1; }
+            if (p.status != TGSF_PIECE_EMIT) continue;
+            const string &raw = b.names[last];
+            const string name = pass >= 2 ? new_seq_name(raw, pass) : raw;
+            pass++;
+            const char *s = (const char *)b.bases + b.offsets[last] + p.start;
+            rec.clear();
+            if (P.Outfq == 1) {
+                const char *q = (const char *)b.quals + b.offsets[last] + p.start;
+                rec += '@'; rec += name; rec += '\n'; rec.append(s, p.len); rec += "\n+\n"; rec.append(q, p.len); rec += '\n';
+            } else {
+                rec += '>'; rec += name; rec += '\n'; rec.append(s, p.len); rec += '\n';
+            }
+            if (P.OUTGZ) {
+                if (gz_member(rec, P.compLevel, gz)) fwrite(gz.data(), 1, gz.size(), out);
+            } else {
+                fwrite(rec.data(), 1, rec.size(), out);
+            }
+            cleanNum++;
+            cleanBases += (uint64_t)p.len;
+        }
+        b.clear();
+    };
+    auto submit = [&](int bi) {
+        Batch &b = ring[(size_t)bi];
+        tgsf_ctx *c = ctx[(size_t)(bi % P.gpus)];
+        if (tgsf_submit(c, b.bases, has_qual ? b.quals : nullptr, b.offsets.data(), b.n()) != TGSF_OK) die_tgsf("tgsf_submit");
+        inflight.push_back(bi);
+        submitted++;
+    };
+    {
+        FastxReader rd(P.InFile);
+        string name, seq, qual;
+        int cur = 0;
+        while (rd.read(name, seq, qual)) {
+            rawNum++;
+            rawBases += seq.size();
+            Batch &b = ring[(size_t)cur];
+            if (!b.add(name, seq, qual, has_qual)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
+            if (b.used >= P.batch_bases) {
+                submit(cur);
+                cur = (cur + 1) % slots;
+                if ((int)inflight.size() == slots) retire(); // the ring slot we are about to fill is free again
+            }
+        }
+        if (ring[(size_t)cur].n()) submit(cur);
+        while (!inflight.empty()) retire();
+    }
+    if (out != stdout) fclose(out);
+
+    // ---- counters: merge over GPUs (T.cpp:3208-3213) and the INFO lines (T.cpp:3214-3235) ----------
+    tgsf_counter_layout L;
+    tgsf_counter_layout_get(ctx[0], &L);
+    std::vector<uint64_t> C(L.n_u64, 0), tmp(L.n_u64);
+    for (tgsf_ctx *c : ctx) {
+        if (tgsf_counters(c, tmp.data(), L.n_u64) != TGSF_OK) die_tgsf("tgsf_counters");
+        for (uint32_t i = 0; i < L.n_u64; i++) C[i] += tmp[i];
+    }
+    const uint64_t *D = C.data() + L.drop_info;
+    cerr << "INFO: " << rawNum << " reads with a total of " << rawBases << " bases were input." << endl;
+    if (!P.OnlyQC) {
+        cerr << "INFO: " << D[0] << " reads were discarded with " << D[1] << " bases due to low quality." << endl;
+        cerr << "INFO: " << D[2] << " reads have adapter at 5', 3' and middle." << endl;
+        cerr << "INFO: " << D[3] << " reads have adapter at 5' and middle." << endl;
+        cerr << "INFO: " << D[4] << " reads have adapter at 3' and middle." << endl;
+        cerr << "INFO: " << D[5] << " reads have adapter at 5' and 3' end." << endl;
+        cerr << "INFO: " << D[6] << " reads only have adapter at middle." << endl;
+        cerr << "INFO: " << D[7] << " reads only have adapter at 5' end." << endl;
+        cerr << "INFO: " << D[8] << " reads only have adapter at 3' end." << endl;
+        cerr << "INFO: " << D[9] << " reads didn't have any adapter." << endl;
+        cerr << "INFO: " << D[10] << " bases were trimmed due to the adapter or base content bias." << endl;
+        cerr << "INFO: " << D[11] << " reads were discarded with " << D[12] << " bases due to the short length." << endl;
+        cerr << "INFO: " << D[13] << " reads were discarded with " << D[14] << " bases due to low quality after split." << endl;
+        if (P.MinRepeat > 0)
+            cerr << "INFO: " << D[15] << " reads were discarded with " << D[16] << " bases due to short repeat length." << endl;
+        cerr << "INFO: " << cleanNum << " reads with a total of " << cleanBases << " bases after filtering." << endl;
+        if (!P.OutFile.empty()) cerr << "INFO: Filtered reads were written to: " << P.OutFile << "." << endl;
+    }
+    if (const char *dump = getenv("TGSF_DUMP_COUNTERS")) { // raw counter block for report tooling / tests
+        FILE *f = fopen(dump, "wb");
+        if (f) {
+            fwrite(&L, sizeof(L), 1, f);
+            fwrite(C.data(), sizeof(uint64_t), C.size(), f);
+            fclose(f);
+        }
+    }
+    for (Batch &b : ring) b.release();
+    for (tgsf_ctx *c : ctx) tgsf_destroy(c);
+    return 0;
+}

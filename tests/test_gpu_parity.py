@@ -290,3 +290,78 @@ def test_full_size_properties_config1():
         r2, p2 = eng.run(again)
     assert (r2["status"] == _capi.READ_EVALUATED).all()
     assert len(p2) == len(em) and (p2["start"] == 0).all() and (p2["len"] == em["len"]).all()
+
+
+# ---- the C++ host CLI (src/tgsfilter) against the reference CLI ---------------------------------
+def _run_host_cli(args, fastq: bytes, in_name="in.fq", out_name="out.fq"):
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "src", "tgsfilter")
+    if not os.path.exists(exe):
+        subprocess.run(["make", "-C", os.path.join(root, "src")], check=True)
+    with tempfile.TemporaryDirectory() as td:
+        fi = os.path.join(td, in_name)
+        with open(fi, "wb") as f:
+            f.write(fastq)
+        cmd = [exe, "-i", fi] + list(args)
+        fo = None
+        if out_name:
+            fo = os.path.join(td, out_name)
+            cmd += ["-o", fo]
+        pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        out = pr.stdout
+        if fo and os.path.exists(fo):
+            with open(fo, "rb") as f:
+                out = f.read()
+        return pr.returncode, out, pr.stderr.decode("utf-8", "replace")
+
+
+def _info(stderr: str):
+    return [l for l in stderr.splitlines()
+            if l.startswith(("INFO", "Warning")) and "written to" not in l and "reset -t" not in l]
+
+
+def test_host_cli_matches_golden_reference_cli_run():
+    import json
+    with open(golden_lib.HERE + "/cli_hifi.json") as f:
+        g = json.load(f)
+    batch = synth.make_config(g["config"], g["n_reads"], max_len=g["max_len"])
+    rc, out, err = _run_host_cli(["-x", "hifi"], batch.to_fastq(), out_name=None)
+    assert rc == 0, err
+    assert out.decode() == g["stdout"]
+    assert _info(err) == g["info"]
+
+
+@pytest.mark.parametrize("cfg,n,args", [
+    (2, 400, ["-x", "ont"]),
+    (3, 60, ["-x", "ont", "-M", "35", "-T", "50", "-D"]),
+    (4, 600, ["-x", "clr", "-q", "7", "-Q", "15", "-e", "150", "-b", "1"]),
+    (5, 300, ["-x", "hifi", "-k", "11", "-p", "40"]),
+    (1, 200, ["-x", "hifi", "-5", "10", "-3", "0", "-l", "500", "-f"]),
+])
+def test_host_cli_vs_reference_cli(cfg, n, args):
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not present")
+    batch = synth.make_config(cfg, n, max_len=120000)
+    fq = batch.to_fastq()
+    out_name = "out.fa" if "-f" in args else "out.fq"
+    r_rc, r_out, r_err, _ = ref_lib.run_cli(args + ["-t", "1"], fq, out_name=out_name)
+    h_rc, h_out, h_err = _run_host_cli(args, fq, out_name=out_name)
+    assert (h_rc, r_rc) == (0, 0), h_err
+    assert h_out == r_out
+    assert _info(h_err) == _info(r_err)
+
+
+def test_host_cli_gzip_in_and_out_roundtrip():
+    import gzip
+    import ref_lib
+    batch = synth.make_config(2, 120, max_len=40000)
+    fq = batch.to_fastq()
+    rc, out_plain, _ = _run_host_cli(["-x", "ont"], fq)
+    rc2, out_gz, err = _run_host_cli(["-x", "ont", "-c", "4"], gzip.compress(fq), in_name="in.fq.gz",
+                                     out_name="out.fq.gz")
+    assert rc == 0 and rc2 == 0, err
+    assert gzip.decompress(out_gz) == out_plain  # one gzip member per record, same bytes inside

@@ -1,0 +1,230 @@
+"""CPU suite for the host side: C-ABI surface (load + exported symbols, loud failure without a
+GPU), record assembly, parameter mirror, pre-pass decisions, sharding and the world_size-2 counter
+all-reduce (gloo)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from tgsfilter_b200 import _capi, prepass, records, shard, synth
+from tgsfilter_b200.params import ADAPTER_LIB, FilterParams, rev_comp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+# ---- C-ABI surface ----------------------------------------------------------------------------
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _capi.load()
+    header = open(os.path.join(ROOT, "include", "tgsf.h")).read()
+    declared = set(re.findall(r"\b(tgsf_[a-z_0-9]+)\s*\(", header))
+    declared -= {"tgsf_make_layout", "tgsf_bins_for_len"}
+    assert declared == set(_capi.EXPORTED_SYMBOLS), declared ^ set(_capi.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert b"sm_100a" in lib.tgsf_version()
+
+
+def test_struct_layouts_match_the_header():
+    assert C.sizeof(_capi.ReadResult) == 32 and np.dtype(_capi.READ_RESULT_DTYPE).itemsize == 32
+    assert C.sizeof(_capi.Piece) == 32 and np.dtype(_capi.PIECE_DTYPE).itemsize == 32
+    assert C.sizeof(_capi.AlignResult) == 32 and np.dtype(_capi.ALIGN_RESULT_DTYPE).itemsize == 32
+    assert C.sizeof(_capi.CounterLayout) == 18 * 4
+
+
+@pytest.mark.skipif(_have_gpu(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_engine_fails_loudly_without_gpu():
+    from tgsfilter_b200.engine import FilterEngine
+    with pytest.raises(_capi.TgsfError) as ei:
+        FilterEngine(synth.config_params(1))
+    assert ei.value.code == _capi.TGSF_ERR_CUDA
+
+
+def test_create_rejects_bad_parameters_before_touching_the_gpu():
+    lib = _capi.load()
+    ctx = C.c_void_p()
+    p = FilterParams(adapters=[b"A" * 300]).apply_read_type("ont")
+    cp, keep = p.to_c()
+    assert lib.tgsf_create(0, C.byref(cp), C.byref(ctx)) == _capi.TGSF_ERR_INVALID
+    assert b"adapter" in lib.tgsf_last_error()
+    p = FilterParams(adapters=[ADAPTER_LIB[0]], kmer=40, min_repeat=5).apply_read_type("hifi")
+    cp, keep = p.to_c()
+    assert lib.tgsf_create(0, C.byref(cp), C.byref(ctx)) == _capi.TGSF_ERR_INVALID
+    p = FilterParams(adapters=[ADAPTER_LIB[0]])  # similarities never defaulted
+    cp, keep = p.to_c()
+    assert lib.tgsf_create(0, C.byref(cp), C.byref(ctx)) == _capi.TGSF_ERR_INVALID
+    assert lib.tgsf_collect(None, None, 0, None, 0, None) == _capi.TGSF_ERR_INVALID
+
+
+def test_counter_layout_is_shared_with_the_oracle():
+    p = FilterParams(bc_len=150, max_read_len=250000)
+    L = oracle_lib.layout(p)
+    assert L.max_bins == 250000 // 100 + 1 and L.bc_len == 150
+    assert L.drop_info == 0 and L.raw_hist == 17 and L.clean_hist == 17 + 256
+    assert L.n_u64 == L.clean_bin_qual + L.max_bins * 5
+    assert L.raw5p_cnt % 8 == 0 and L.raw_bin_cnt % 8 == 0
+
+
+# ---- records ----------------------------------------------------------------------------------
+def test_new_seq_name_inserts_before_first_whitespace():
+    assert records.new_seq_name(b"read1", 2) == b"read1:2"
+    assert records.new_seq_name(b"read1 runid=7 ch=2", 3) == b"read1:3 runid=7 ch=2"
+    assert records.new_seq_name(b"r\tx y", 2) == b"r:2\tx y"
+    assert records.new_seq_name(b"", 2) == b":2"
+
+
+def test_format_records_numbers_only_emitted_pieces():
+    batch = synth.pack_reads([b"ACGTACGTAC", b"GGGGGCCCCC"], [b"IIIIIIIIII", b"5555555555"],
+                             [b"a desc", b"b"])
+    pieces = np.zeros(4, dtype=_capi.PIECE_DTYPE)
+    pieces["read"] = [0, 0, 0, 1]
+    pieces["start"] = [0, 3, 6, 2]
+    pieces["len"] = [2, 2, 4, 5]
+    pieces["status"] = [_capi.PIECE_EMIT, _capi.PIECE_LOWQ, _capi.PIECE_EMIT, _capi.PIECE_EMIT]
+    recs = records.format_records(batch, pieces)
+    assert [r[1] for r in recs] == [b"a desc", b"a:2 desc", b"b"]
+    assert recs[1][0] == b"@a:2 desc\nGTAC\n+\nIIII\n"
+    assert records.format_records(batch, pieces, fastq=False)[2][0] == b">b\nGGGCC\n"
+
+
+# ---- params -----------------------------------------------------------------------------------
+def test_rev_comp_follows_the_reference_table():
+    assert rev_comp(b"ACGTNacgtRYKMxz") == b"NNKMRYacgtNACGT"
+    assert rev_comp(ADAPTER_LIB[0]) == ADAPTER_LIB[1]
+    assert rev_comp(ADAPTER_LIB[8]) == ADAPTER_LIB[9]
+
+
+def test_read_type_defaults():
+    p = FilterParams().apply_read_type("hifi")
+    assert (np.float32(p.mid_sim), np.float32(p.end_sim)) == (np.float32(0.95), np.float32(0.9))
+    p = FilterParams(end_sim=0.7).apply_read_type("ont")
+    assert (np.float32(p.mid_sim), np.float32(p.end_sim)) == (np.float32(0.9), np.float32(0.7))
+    assert FilterParams().end_match_len == 4  # constructor default, not the usage text's 15
+
+
+# ---- pre-pass host logic ----------------------------------------------------------------------
+def test_base_content_trim_matches_oracle_on_random_counts():
+    rng = np.random.default_rng(4)
+    for trial in range(40):
+        n = int(rng.integers(50, 5000))
+        check = int(rng.integers(100, 200))
+        base = rng.multinomial(n, [0.25] * 4, size=check).astype(np.int32)
+        if trial % 2:
+            base[: int(rng.integers(1, 30))] += rng.integers(0, n // 10 + 2, 4).astype(np.int32)
+        bias = float([1.0, 0.5, 2.0, 5.0][trial % 4])
+        assert prepass.base_content_trim(base, n, bias) == oracle_lib.base_content_trim(base, n, bias)
+
+
+def test_qtype_and_default_min_q():
+    assert prepass.get_qtype(34, 73) == 33
+    assert prepass.get_qtype(66, 104) == 33 and prepass.get_qtype(80, 104) == 64
+    assert prepass.get_qtype(50, 130) == 33 and prepass.get_qtype(60, 130) == 64
+    assert prepass.default_min_q(-1, 40, "hifi") == 20 and prepass.default_min_q(-1, 15, "hifi") == 0
+    assert prepass.default_min_q(-1, 40, "clr") == 10 and prepass.default_min_q(7.5, 40, "ont") == 7.5
+
+
+def test_adapter_selection_rules():
+    z = np.zeros(22, dtype=np.int64)
+    c = np.zeros((150, 4), dtype=np.int32)
+    # nothing found -> read-type fallback
+    r = prepass.resolve(c, c, z, z, n=100, end_bias=1.0, mid_sim=0.9, bc_len=150, read_type="ont")
+    assert r.adapters == [ADAPTER_LIB[8], ADAPTER_LIB[9]] and r.adapter5p == b""
+    r = prepass.resolve(c, c, z, z, n=100, end_bias=1.0, mid_sim=0.95, bc_len=150, read_type="hifi")
+    assert r.adapters == [ADAPTER_LIB[0], ADAPTER_LIB[1]]
+    # a strong 5' adapter suppresses a > 5x weaker 3' one (T.cpp:3086-3092)
+    m5, m3 = z.copy(), z.copy()
+    m5[8] = 50 * 1000
+    m3[4] = 28 * 150
+    r = prepass.resolve(c, c, m5, m3, n=100, end_bias=1.0, mid_sim=0.9, bc_len=150, read_type="ont")
+    assert r.adapter5p == ADAPTER_LIB[8] and r.adapter3p == b""
+    assert r.adapters == [ADAPTER_LIB[8], ADAPTER_LIB[9]]
+    # depth below 2*minSim is ignored (T.cpp:1193)
+    m5 = z.copy()
+    m5[8] = 50
+    r = prepass.resolve(c, c, m5, z, n=100, end_bias=1.0, mid_sim=0.9, bc_len=150, read_type="clr")
+    assert r.adapter5p == b"" and r.adapters == [ADAPTER_LIB[0], ADAPTER_LIB[1]]
+    # explicit trims win over the base-content scan
+    r = prepass.resolve(c, c, z, z, n=100, end_bias=1.0, mid_sim=0.9, bc_len=150, read_type="ont",
+                        head_trim=0, tail_trim=12)
+    assert (r.trim5p, r.trim3p) == (0, 12)
+
+
+def test_sample_ends_follows_the_prepass_reader():
+    batch = synth.make_config(1, 40, max_len=3000)
+    p = FilterParams()
+    e5, e3, mn, mx, check = prepass.sample_ends(batch, p)
+    assert check == 150 and e5.shape == e3.shape and e5.shape[1] == 150
+    lens = np.diff(batch.offsets.astype(np.int64))
+    keep = np.nonzero(lens >= 1000)[0]
+    assert e5.shape[0] == len(keep)
+    b0, _ = batch.read(int(keep[0]))
+    assert e5[0].tobytes() == b0[:150].tobytes()
+    assert e3[0].tobytes() == rev_comp(b0[-150:].tobytes())
+    assert 33 <= mn <= mx <= 33 + 60
+
+
+# ---- sharding + counter all-reduce ------------------------------------------------------------
+def test_split_batches_covers_every_read_once():
+    batch = synth.make_config(2, 300, max_len=50000)
+    bs = shard.split_batches(batch.offsets, 1_000_000)
+    assert bs[0][0] == 0 and bs[-1][1] == batch.n_reads
+    assert all(a[1] == b[0] for a, b in zip(bs[:-1], bs[1:]))
+    assert all(hi > lo for lo, hi in bs)
+    sizes = [int(batch.offsets[hi] - batch.offsets[lo]) for lo, hi in bs[:-1]]
+    assert all(s <= 1_000_000 + 50000 for s in sizes)
+    dealt = sorted(x for r in range(3) for x in shard.rank_batches(bs, r, 3))
+    assert [d[1:] for d in dealt] == bs
+    # degenerate: one read larger than the target
+    bs1 = shard.split_batches(np.array([0, 10, 5000, 5010], dtype=np.uint64), 100)
+    assert bs1 == [(0, 1), (1, 2), (2, 3)]
+
+
+def _gloo_worker(rank, world, port, ret):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    batch = synth.make_config(1, 60, max_len=4000)
+    params = synth.config_params(1)
+    params.head_trim = 5
+    params.max_read_len = 8000
+    cnt = np.zeros(oracle_lib.layout(params).n_u64, dtype=np.uint64)
+    for _, lo, hi in shard.rank_batches(shard.split_batches(batch.offsets, 40_000), rank, world):
+        _, _, cnt = oracle_lib.run(params, batch.slice(lo, hi), cnt)
+    flat = torch.from_numpy(cnt.view(np.int64))
+    shard.allreduce_counters(flat)
+    if rank == 0:
+        ret.put(flat.numpy().view(np.uint64).copy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_world_size_2_counters_allreduce_equals_single_process():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    merged = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    batch = synth.make_config(1, 60, max_len=4000)
+    params = synth.config_params(1)
+    params.head_trim = 5
+    params.max_read_len = 8000
+    _, _, single = oracle_lib.run(params, batch)
+    np.testing.assert_array_equal(merged, single)
