@@ -491,8 +491,8 @@ def main():
                    "head_trim": params.head_trim, "tail_trim": params.tail_trim,
                    "l2": "inputs (2 B/base, >= 0.5 GB per launch) are larger than the 126 MB L2",
                    "timing": "CUDA events on the library stream around the K1..K5 sequence, max over ranks"},
-        "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(2 * n_bases + 8 * (n_reads + len(sub))),
-                "d2h_bytes_per_step": int(d2h_bytes), "chunks": len(sub), "slots": 2},
+        "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(2 * n_bases + 8 * (n_reads + len(sub))) * world,
+                "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

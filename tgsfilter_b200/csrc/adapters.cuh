@@ -74,7 +74,8 @@ static __device__ void mid_chunk_record(const u64 *__restrict__ tab, int tab_str
 template <int NW, int AP>
 __global__ void __launch_bounds__(MID_THREADS)
 k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__restrict__ chunks,
-               const u32 *__restrict__ n_chunks_ptr, uint8_t *__restrict__ chunk_min,
+               const u32 *__restrict__ perm, const u32 *__restrict__ n_chunks_ptr,
+               uint8_t *__restrict__ chunk_min,
                u32 *__restrict__ chunk_cnt, u64 *__restrict__ chunk_first,
                u32 *__restrict__ best_mid) {
     const u32 n_chunks = *n_chunks_ptr; // device-side total (chunk_off[n_reads])
@@ -98,8 +99,9 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
     }
     const uint4 *__restrict__ b16 = (const uint4 *)B.bases;
 
-    for (u32 ci = blockIdx.x * MID_THREADS + threadIdx.x; ci < n_chunks;
-         ci += gridDim.x * MID_THREADS) {
+    for (u32 it = blockIdx.x * MID_THREADS + threadIdx.x; it < n_chunks;
+         it += gridDim.x * MID_THREADS) {
+        const u32 ci = perm[it]; // length-descending order: a warp's 32 chunks have the same length
         const ChunkEntry ce = chunks[ci];
         const u64 rs = B.offsets[ce.read];
         const u64 re = B.offsets[ce.read + 1];
@@ -204,20 +206,29 @@ static __device__ void mid_for_each_end(const DevBatch &B, const AdapterTables &
                                         const DevAdapter &A, int a, int end_len, int chunk_shift,
                                         u32 r, int d, const u32 *__restrict__ chunk_off,
                                         const ChunkEntry *__restrict__ chunks, u32 chunk_stride,
-                                        const uint8_t *__restrict__ chunk_min, F f) {
+                                        const uint8_t *__restrict__ chunk_min,
+                                        const u32 *__restrict__ chunk_hits,
+                                        const u64 *__restrict__ chunk_first, F f) {
     const u64 rs = B.offsets[r], re = B.offsets[r + 1];
     const u64 mb = rs + (u64)end_len, me = re - (u64)end_len;
     for (u32 ci = chunk_off[r]; ci < chunk_off[r + 1]; ++ci) {
-        if (chunk_min[(u64)a * chunk_stride + ci] != (uint8_t)min(d, 254)) continue;
+        const u64 slot = (u64)a * chunk_stride + ci;
+        if (chunk_min[slot] != (uint8_t)min(d, 254)) continue;
+        const u64 rec = chunk_first[slot]; // first column scoring the chunk minimum | minimum << 48
+        if ((int)(rec >> 48) != d) continue;
+        const u64 first = rec & ((1ull << 48) - 1);
+        u32 left = chunk_hits[slot];
         const u64 cb = (u64)chunks[ci].chunk << chunk_shift;
-        const u64 ob = max(cb, mb), oe = min(cb + (1ull << chunk_shift), me);
-        u64 sb = ob > (u64)A.halo_mid ? ob - (u64)A.halo_mid : 0;
+        const u64 oe = min(cb + (1ull << chunk_shift), me);
+        // restart a halo before the first location (exact from `first` on), stop after the last
+        u64 sb = first > (u64)A.halo_mid ? first - (u64)A.halo_mid : 0;
         if (sb < mb) sb = mb;
         Myers<NW> s;
         myers_init_hw<NW>(s, T.qlen);
-        for (u64 p = sb; p < oe; ++p) {
+        for (u64 p = sb; p < oe && left; ++p) {
             myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(B.bases + p) * NW, 0);
-            if (p >= ob && s.score == d) {
+            if (p >= first && s.score == d) {
+                --left;
                 if (!f(p)) return;
             }
         }
@@ -269,7 +280,8 @@ __global__ void __launch_bounds__(RES_THREADS)
 k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int chunk_shift, int extra_len,
            int n_adapters, const u32 *__restrict__ best_mid, const u32 *__restrict__ chunk_off,
            const ChunkEntry *__restrict__ chunks, u32 chunk_stride,
-           const uint8_t *__restrict__ chunk_min, const u32 *__restrict__ mid_n,
+           const uint8_t *__restrict__ chunk_min, const u32 *__restrict__ chunk_hits,
+           const u64 *__restrict__ chunk_first, const u32 *__restrict__ mid_n,
            const u32 *__restrict__ mid_off, Region *__restrict__ pool,
            const u32 *__restrict__ dev_status) {
     if (*dev_status != DEV_STATUS_OK) return;
@@ -287,7 +299,7 @@ k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int chunk_shift, int ex
         Region *out = pool + mid_off[key];
         u32 i = 0;
         mid_for_each_end<NW>(B, T, A, a, end_len, chunk_shift, r, d, chunk_off, chunks, chunk_stride,
-                             chunk_min, [&](u64 p) {
+                             chunk_min, chunk_hits, chunk_first, [&](u64 p) {
                                  const u64 s0 = shw_start<NW>(T, B.bases, mb, p, d);
                                  int ts = (int)(s0 - rs) - extra_len;       // T.cpp:1248,1253
                                  int te = (int)(p - rs) + 1 + extra_len;    // T.cpp:1249,1254

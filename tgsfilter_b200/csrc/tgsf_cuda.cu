@@ -196,7 +196,7 @@ struct Slot {
     bool has_qual = false;
     // work arrays
     DBuf seg_start, seg_len, seg_sum, seg_flag, tile_cnt, tile_off, tiles;
-    DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first;
+    DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first, chunk_perm, chunk_hist;
     int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
     DBuf scan_tmp;
@@ -263,7 +263,7 @@ int slot_init(Slot &s) {
 void slot_release(Slot &s) {
     DBuf *bufs[] = {&s.in_bases, &s.in_quals, &s.in_offsets, &s.seg_start, &s.seg_len, &s.seg_sum,
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
-                    &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first,
+                    &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
                     &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.scratch.buf};
     for (DBuf *b : bufs) b->release();
@@ -308,6 +308,8 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.chunk_min.ensure((size_t)s.chunks_cap * (size_t)A));
     TRY(s.chunk_hits.ensure((size_t)s.chunks_cap * (size_t)A * sizeof(u32)));
     TRY(s.chunk_first.ensure((size_t)s.chunks_cap * (size_t)A * sizeof(u64)));
+    TRY(s.chunk_perm.ensure((size_t)s.chunks_cap * sizeof(u32)));
+    TRY(s.chunk_hist.ensure(CHUNK_BUCKETS * sizeof(u32)));
     TRY(s.best_mid.ensure(((size_t)n * A + 1) * sizeof(u32)));
     TRY(s.mid_n.ensure(((size_t)n * A + 1) * sizeof(u32)));
     TRY(s.mid_off.ensure(((size_t)n * A + 2) * sizeof(u32)));
@@ -440,6 +442,14 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                            s.scan_tmp.cap / sizeof(u32)));
         k_fill_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.chunk_off.as<u32>(), P.end_len, s.chunk_shift, s.chunks.as<ChunkEntry>());
         c->launches++;
+        CU(cudaMemsetAsync(s.chunk_hist.p, 0, CHUNK_BUCKETS * sizeof(u32), st));
+        k_chunk_hist<<<cdiv(n, UTIL_THREADS), UTIL_THREADS, 0, st>>>(s.B, s.chunk_off.as<u32>(), s.chunks.as<ChunkEntry>(),
+                                                                   P.end_len, s.chunk_shift, s.chunk_hist.as<u32>());
+        k_chunk_base<<<1, 32, 0, st>>>(s.chunk_hist.as<u32>());
+        k_chunk_scatter<<<cdiv(n, UTIL_THREADS), UTIL_THREADS, 0, st>>>(s.B, s.chunk_off.as<u32>(), s.chunks.as<ChunkEntry>(),
+                                                                      P.end_len, s.chunk_shift, s.chunk_hist.as<u32>(),
+                                                                      s.chunk_perm.as<u32>());
+        c->launches += 3;
         const AdapterCtx AC = c->ads.ctx();
         const u32 *n_chunks_ptr = s.chunk_off.as<u32>() + n;
         const int res_grid = c->sm_count * 4;
@@ -461,12 +471,14 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                     constexpr int NW = decltype(nwc)::value;
                     if (pair)
                         k_mid_scan_dyn<NW, 2><<<c->sm_count * 8, MID_THREADS, 256 * 2 * NW * sizeof(u64), st>>>(
-                            s.B, AC, M, s.chunks.as<ChunkEntry>(), n_chunks_ptr, s.chunk_min.as<uint8_t>(),
-                            s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(), s.best_mid.as<u32>());
+                            s.B, AC, M, s.chunks.as<ChunkEntry>(), s.chunk_perm.as<u32>(), n_chunks_ptr,
+                            s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
+                            s.best_mid.as<u32>());
                     else
                         k_mid_scan_dyn<NW, 1><<<c->sm_count * 8, MID_THREADS, 256 * NW * sizeof(u64), st>>>(
-                            s.B, AC, M, s.chunks.as<ChunkEntry>(), n_chunks_ptr, s.chunk_min.as<uint8_t>(),
-                            s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(), s.best_mid.as<u32>());
+                            s.B, AC, M, s.chunks.as<ChunkEntry>(), s.chunk_perm.as<u32>(), n_chunks_ptr,
+                            s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
+                            s.best_mid.as<u32>());
                     c->launches++;
                     return check_launch("k_mid_scan");
                 }));
@@ -528,8 +540,8 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
                 constexpr int NW = decltype(nwc)::value;
                 k_mid_emit<NW><<<res_grid, RES_THREADS, 0, st>>>(
                     s.B, AC, a, P.end_len, s.chunk_shift, P.extra_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
-                    s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.mid_n.as<u32>(),
-                    s.mid_off.as<u32>(), s.pool.as<Region>(), &H->status);
+                    s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(),
+                    s.chunk_first.as<u64>(), s.mid_n.as<u32>(), s.mid_off.as<u32>(), s.pool.as<Region>(), &H->status);
                 c->launches++;
                 return check_launch("k_mid_emit");
             }));

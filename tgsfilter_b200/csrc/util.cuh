@@ -135,6 +135,68 @@ __global__ void k_fill_chunks(DevBatch B, const u32 *__restrict__ chunk_off, int
     }
 }
 
+// Length-descending permutation of the chunk table (counting sort over 64 length buckets, block
+// aggregated).  k_mid_scan walks the chunks in this order so that the 32 lanes of a warp (and the
+// CTAs of a wave) work on chunks of the same length: ~30 % of the absolute chunks are partial
+// (first / last of a read's window) and would otherwise idle their warp for half a chunk.
+#define CHUNK_BUCKETS 64
+static __device__ __forceinline__ u32 chunk_bucket(const DevBatch &B, u32 r, u32 chunk, int end_len,
+                                                   int chunk_shift) {
+    const u64 mb = B.offsets[r] + (u64)end_len, me = B.offsets[r + 1] - (u64)end_len;
+    const u64 cb = (u64)chunk << chunk_shift;
+    const u64 ob = max(cb, mb), oe = min(cb + (1ull << chunk_shift), me);
+    const u32 len = (u32)(oe - ob);
+    return (CHUNK_BUCKETS - 1) - ((len - 1) >> (chunk_shift - 6)); // bucket 0 = longest
+}
+
+__global__ void __launch_bounds__(UTIL_THREADS)
+k_chunk_hist(DevBatch B, const u32 *__restrict__ chunk_off, const ChunkEntry *__restrict__ chunks,
+             int end_len, int chunk_shift, u32 *__restrict__ hist) {
+    __shared__ u32 h[CHUNK_BUCKETS];
+    if (threadIdx.x < CHUNK_BUCKETS) h[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 r = blockIdx.x * UTIL_THREADS + threadIdx.x;
+    if (r < B.n_reads)
+        for (u32 t = chunk_off[r]; t < chunk_off[r + 1]; ++t)
+            atomicAdd(&h[chunk_bucket(B, r, chunks[t].chunk, end_len, chunk_shift)], 1u);
+    __syncthreads();
+    if (threadIdx.x < CHUNK_BUCKETS && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// hist[64] -> exclusive prefix in place (cursor of each bucket)
+__global__ void k_chunk_base(u32 *__restrict__ hist) {
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (int b = 0; b < CHUNK_BUCKETS; ++b) {
+            const u32 c = hist[b];
+            hist[b] = acc;
+            acc += c;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(UTIL_THREADS)
+k_chunk_scatter(DevBatch B, const u32 *__restrict__ chunk_off, const ChunkEntry *__restrict__ chunks,
+                int end_len, int chunk_shift, u32 *__restrict__ cursor, u32 *__restrict__ perm) {
+    __shared__ u32 cnt[CHUNK_BUCKETS], base[CHUNK_BUCKETS];
+    if (threadIdx.x < CHUNK_BUCKETS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const u32 r = blockIdx.x * UTIL_THREADS + threadIdx.x;
+    const u32 b0 = r < B.n_reads ? chunk_off[r] : 0, b1 = r < B.n_reads ? chunk_off[r + 1] : 0;
+    for (u32 t = b0; t < b1; ++t) atomicAdd(&cnt[chunk_bucket(B, r, chunks[t].chunk, end_len, chunk_shift)], 1u);
+    __syncthreads();
+    if (threadIdx.x < CHUNK_BUCKETS) {
+        const u32 c = cnt[threadIdx.x];
+        base[threadIdx.x] = c ? atomicAdd(&cursor[threadIdx.x], c) : 0u;
+        cnt[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (u32 t = b0; t < b1; ++t) {
+        const u32 k = chunk_bucket(B, r, chunks[t].chunk, end_len, chunk_shift);
+        perm[base[k] + atomicAdd(&cnt[k], 1u)] = t;
+    }
+}
+
 __global__ void k_check_pool(const u32 *__restrict__ pool_total, u32 pool_cap,
                              u32 *__restrict__ dev_status) {
     if (*pool_total > pool_cap) *dev_status = DEV_STATUS_POOL_OVERFLOW;
