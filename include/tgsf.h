@@ -179,6 +179,11 @@ int tgsf_counters(tgsf_ctx *ctx, uint64_t *out, uint32_t n_u64);
 int tgsf_counters_reset(tgsf_ctx *ctx);
 /* Device address of the counter block (n_u64 words) for an in-place NCCL allreduce(sum). */
 int tgsf_counters_device(tgsf_ctx *ctx, void **d_ptr, uint32_t *n_u64);
+/* Single-process multi-GPU: sums the counter blocks of n contexts (one per GPU) over peer copies
+ * (NVLink where peer access is available) and leaves the total in every context.  Replaces the
+ * per-thread merge loop T.cpp:3208-3213 across devices.  Multi-process jobs use an NCCL allreduce
+ * on tgsf_counters_device instead (bench.py). */
+int tgsf_allreduce(tgsf_ctx **ctxs, int n);
 /* Number of kernels launched by this context since create (bench.py's gpu_launches). */
 uint64_t tgsf_launch_count(const tgsf_ctx *ctx);
 

@@ -623,11 +623,9 @@ int main(int argc, char **argv) {
     // ---- counters: merge over GPUs (T.cpp:3208-3213) and the INFO lines (T.cpp:3214-3235) ----------
     tgsf_counter_layout L;
     tgsf_counter_layout_get(ctx[0], &L);
-    std::vector<uint64_t> C(L.n_u64, 0), tmp(L.n_u64);
-    for (tgsf_ctx *c : ctx) {
-        if (tgsf_counters(c, tmp.data(), L.n_u64) != TGSF_OK) die_tgsf("tgsf_counters");
-        for (uint32_t i = 0; i < L.n_u64; i++) C[i] += tmp[i];
-    }
+    std::vector<uint64_t> C(L.n_u64, 0);
+    if (tgsf_allreduce(ctx.data(), (int)ctx.size()) != TGSF_OK) die_tgsf("tgsf_allreduce");
+    if (tgsf_counters(ctx[0], C.data(), L.n_u64) != TGSF_OK) die_tgsf("tgsf_counters");
     const uint64_t *D = C.data() + L.drop_info;
     cerr << "INFO: " << rawNum << " reads with a total of " << rawBases << " bases were input." << endl;
     if (!P.OnlyQC) {

@@ -365,3 +365,30 @@ def test_host_cli_gzip_in_and_out_roundtrip():
                                      out_name="out.fq.gz")
     assert rc == 0 and rc2 == 0, err
     assert gzip.decompress(out_gz) == out_plain  # one gzip member per record, same bytes inside
+
+
+def test_tgsf_allreduce_sums_context_blocks():
+    import ctypes as C
+    batch = synth.make_config(1, 120, max_len=6000)
+    params = synth.config_params(1)
+    params.max_read_len = 8000
+    _, _, o_cnt = oracle_lib.run(params, batch)
+    lib = _capi.load()
+    n_dev = 1
+    try:
+        import torch
+        n_dev = max(1, torch.cuda.device_count())
+    except Exception:
+        pass
+    engines = [FilterEngine(params, device=(i % n_dev)) for i in range(3)]
+    try:
+        bounds = [0, 40, 90, 120]
+        for e, lo, hi in zip(engines, bounds[:-1], bounds[1:]):
+            e.run(batch.slice(lo, hi))
+        arr = (C.c_void_p * 3)(*[e._ctx for e in engines])
+        _capi.check(lib.tgsf_allreduce(arr, 3), "tgsf_allreduce")
+        for e in engines:
+            assert np.array_equal(e.counters().flat, o_cnt)
+    finally:
+        for e in engines:
+            e.close()

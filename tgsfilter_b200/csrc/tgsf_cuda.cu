@@ -924,6 +924,48 @@ int tgsf_counters_device(tgsf_ctx *c, void **d_ptr, uint32_t *n_u64) {
 
 uint64_t tgsf_launch_count(const tgsf_ctx *c) { return c ? c->launches : 0; }
 
+int tgsf_allreduce(tgsf_ctx **ctxs, int n) {
+    if (!ctxs || n <= 0) { set_err("allreduce: no contexts"); return TGSF_ERR_INVALID; }
+    for (int i = 0; i < n; ++i) {
+        if (!ctxs[i]) { set_err("allreduce: NULL context"); return TGSF_ERR_INVALID; }
+        if (ctxs[i]->outstanding) { set_err("allreduce: collect all batches first"); return TGSF_ERR_STATE; }
+        if (ctxs[i]->P.L.n_u64 != ctxs[0]->P.L.n_u64) { set_err("allreduce: counter layouts differ"); return TGSF_ERR_INVALID; }
+    }
+    if (n == 1) return TGSF_OK;
+    tgsf_ctx *root = ctxs[0];
+    const u32 words = root->P.L.n_u64;
+    const size_t bytes = (size_t)words * sizeof(u64);
+    CU(cudaSetDevice(root->device));
+    for (int i = 1; i < n; ++i) { // direct NVLink path where the topology allows it
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, root->device, ctxs[i]->device) == cudaSuccess && can) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[i]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { /* staged copy still works */ }
+            cudaGetLastError();
+        }
+    }
+    DBuf scratch;
+    TRY(scratch.ensure(bytes));
+    int rc = TGSF_OK;
+    for (int i = 1; i < n && rc == TGSF_OK; ++i) {
+        if (cudaMemcpyPeer(scratch.p, root->device, ctxs[i]->counters.p, ctxs[i]->device, bytes) != cudaSuccess) {
+            set_err("allreduce: peer copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = TGSF_ERR_CUDA;
+            break;
+        }
+        k_add_u64<<<root->sm_count, 256>>>(root->counters.as<u64>(), scratch.as<u64>(), words);
+        root->launches++;
+        if (cudaDeviceSynchronize() != cudaSuccess) { set_err("allreduce: add kernel failed"); rc = TGSF_ERR_CUDA; }
+    }
+    for (int i = 1; i < n && rc == TGSF_OK; ++i)
+        if (cudaMemcpyPeer(ctxs[i]->counters.p, ctxs[i]->device, root->counters.p, root->device, bytes) != cudaSuccess) {
+            set_err("allreduce: broadcast failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = TGSF_ERR_CUDA;
+        }
+    scratch.release();
+    return rc;
+}
+
 int tgsf_prepass(int device, const uint8_t *ends5p, const uint8_t *ends3p, uint32_t n, uint32_t row_len,
                  const uint8_t *const *lib_seq, const int32_t *lib_len, int32_t n_lib, float min_sim,
                  int32_t *bases_num5p, int32_t *bases_num3p, int64_t *map5p, int64_t *map3p) {

@@ -201,3 +201,8 @@ __global__ void k_check_pool(const u32 *__restrict__ pool_total, u32 pool_cap,
                              u32 *__restrict__ dev_status) {
     if (*pool_total > pool_cap) *dev_status = DEV_STATUS_POOL_OVERFLOW;
 }
+
+// dst[i] += src[i]: the reduction step of tgsf_allreduce (counter blocks of peer GPUs).
+__global__ void k_add_u64(u64 *__restrict__ dst, const u64 *__restrict__ src, u32 n) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
+}
