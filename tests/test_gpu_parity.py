@@ -392,3 +392,52 @@ def test_tgsf_allreduce_sums_context_blocks():
     finally:
         for e in engines:
             e.close()
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_randomised_parameters_vs_oracle(seed):
+    """Parameter fuzz: adapter sets with mixed word counts, every threshold, both k-mer key widths,
+    the wide (global-atomic) 5'/3' tables, FASTA input, discard, tiny and huge trims."""
+    rng = np.random.default_rng(1000 + seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def rnd(n):
+        return acgt[rng.integers(0, 4, n)].tobytes()
+
+    n_ad = int(rng.integers(1, 5))
+    ads = []
+    for _ in range(n_ad):
+        ql = int([22, 28, 45, 50, 64, 65, 100, 130, 200][int(rng.integers(0, 9))])
+        a = rnd(ql)
+        ads += [a, rev_comp(a)] if rng.random() < 0.6 else [a]
+    seqs, quals = [], []
+    for i in range(int(rng.integers(30, 90))):
+        L = int(rng.integers(1, 6000))
+        s = bytearray(rnd(L))
+        for _ in range(int(rng.integers(0, 3))):
+            a = ads[int(rng.integers(0, len(ads)))]
+            m = synth.mutate(a, float(rng.random() * 0.15), rng)
+            if L > len(m) + 2:
+                where = int(rng.integers(0, 3))
+                pos = 0 if where == 0 else (L - len(m) if where == 1 else int(rng.integers(0, L - len(m))))
+                s[pos:pos + len(m)] = m
+        if rng.random() < 0.2:
+            for p in rng.integers(0, L, max(1, L // 50)):
+                s[int(p)] = b"NnacgtRY"[int(rng.integers(0, 8))]
+        seqs.append(bytes(s[:L]))
+        mq = rng.normal(20, 8)
+        quals.append((np.clip(np.rint(rng.normal(mq, 5, L)), 0, 60).astype(np.uint8) + 33).tobytes())
+    fasta = seed % 5 == 4
+    batch = synth.pack_reads(seqs, None if fasta else quals)
+    end_sim = float(rng.choice([0.7, 0.75, 0.8, 0.9, 1.0]))
+    mid_sim = float(rng.choice([0.8, 0.9, 0.95, 1.0]))
+    params = FilterParams(
+        min_len=int(rng.choice([100, 300, 1000])), max_len=int(rng.choice([2147483647, 4000])),
+        min_q=float(rng.choice([0.0, 10.0, 18.5])), max_q=float(rng.choice([255.0, 30.0])),
+        bc_len=int(rng.choice([1, 50, 150, 300])), head_trim=int(rng.choice([0, 0, 7, 5000])),
+        tail_trim=int(rng.choice([0, 0, 3, 120])), end_len=int(rng.choice([20, 150, 400])),
+        end_match_len=int(rng.choice([1, 4, 15, 40])), mid_match_len=int(rng.choice([10, 20, 35, 60])),
+        extra_len=int(rng.choice([0, 50, 200])), end_sim=end_sim, mid_sim=mid_sim,
+        kmer=int(rng.choice([5, 11, 15, 16, 21, 31])), min_repeat=int(rng.choice([0, 0, 3, 30])),
+        qtype=0 if fasta else 33, discard=bool(rng.random() < 0.3), adapters=ads, max_read_len=10000)
+    _compare(params, batch)
