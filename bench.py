@@ -362,6 +362,35 @@ def main():
             sub.append((int(offsets[a]), int(b - a), o_t, int(offsets[b] - offsets[a])))
     d2h_bytes = 0
 
+    # 2-bit packed copy of every sub-batch (what the C++ host's parser produces with tgsf_pack_bases;
+    # the synthetic bases are pure upper-case ACGT, so the exception list is empty)
+    pk_off = [0]
+    for _, _, _, nb in sub:
+        pk_off.append(pk_off[-1] + ((nb + 3) // 4 + 63) // 64 * 64)
+    h_packed = torch.empty(pk_off[-1] + 64, dtype=torch.uint8, pin_memory=True)
+    for (s0, nr, o_t, nb), po in zip(sub, pk_off[:-1]):
+        b = d_bases[s0:s0 + nb]
+        if nb % 4:
+            b = torch.cat([b, torch.full((4 - nb % 4,), 65, dtype=torch.uint8, device=device)])
+        code = (b >> 1) & 3
+        code = (code ^ (code >> 1)).view(-1, 4)          # A0 C1 G2 T3
+        pk = code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)
+        h_packed[po:po + pk.numel()].copy_(pk)
+        del b, code, pk
+    torch.cuda.synchronize()
+
+    def step_e2e_packed():
+        inflight = 0
+        for (s0, nr, o_t, nb), po in zip(sub, pk_off[:-1]):
+            if inflight == 2:
+                eng.collect()
+                inflight -= 1
+            eng.submit_packed_raw(h_packed.data_ptr() + po, h_quals.data_ptr() + s0, o_t.data_ptr(), nr)
+            inflight += 1
+        while inflight:
+            eng.collect()
+            inflight -= 1
+
     def step_e2e():
         nonlocal d2h_bytes
         d2h = 0
@@ -383,6 +412,7 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     step_e2e()
+    step_e2e_packed()
     eng.reset_counters()
 
     # ---- timed: resident
@@ -419,6 +449,24 @@ def main():
         dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
     e2e_s = float(t_e2e.item())
 
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e_packed()
+    barrier()
+    t_pk = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_pk, op=dist.ReduceOp.MAX)
+    e2e_packed_s = float(t_pk.item())
+    # host packer speed (one thread), for context
+    nb_probe = min(n_bases, 256 << 20)
+    probe_out = np.empty(nb_probe // 4 + 16, dtype=np.uint8)
+    ne = __import__("ctypes").c_uint64(0)
+    tp0 = time.perf_counter()
+    _capi.load().tgsf_pack_bases(h_bases.data_ptr(), nb_probe, probe_out.ctypes.data, None, None, 0,
+                                 __import__("ctypes").byref(ne))
+    pack_gbs = nb_probe / (time.perf_counter() - tp0) / 1e9
+
     # ---- final counter allreduce over NVLink (outside the timed region; reported)
     allreduce_ms = None
     if world > 1:
@@ -436,6 +484,7 @@ def main():
     total_bases = n_bases * world
     value = total_bases * args.steps / (dev_ms_max / 1e3) / 1e9
     e2e_value = total_bases * args.steps / e2e_s / 1e9
+    e2e_packed_value = total_bases * args.steps / e2e_packed_s / 1e9
 
     # ---- rooflines
     peaks = {}
@@ -490,6 +539,22 @@ def main():
                "achieved": kept_bases / (kmer_ms / 1e3) / 1e9 if kmer_ms > 0 else 0.0, "peak": None,
                "unit": "Ginserts/s", "frac": None, "traffic": None, "work": "1 insert per kept base",
                "ms": kmer_ms, "share_of_step": kmer_ms / step_ms if step_ms else None}
+    # measured DRAM traffic per launch (one ncu --set full capture of this same command, committed
+    # under profiles/); only valid for the workload it was captured on
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)
+        if tr.get("config") == cfg and tr.get("reads_per_gpu") == n_reads:
+            rl_mid["traffic"] = tr["k_mid_scan"]["dram_bytes"]
+            mid_all = lens - 2 * E
+            qmin = min(len(a) for a in params.adapters)
+            # 1 B per middle-window column of the reads that pass -q/-Q; one pass serves both adapters
+            rl_mid["algorithmic_bytes"] = int(int(mid_all[mid_all >= qmin].sum()) * active_frac)
+            rl_raw["traffic"] = tr["k_scan_tiles_raw"]["dram_bytes"]
+            rl_raw["algorithmic_bytes"] = 2 * n_bases
+            rl_clean["traffic"] = tr["k_scan_tiles_clean"]["dram_bytes"]
+    except Exception:
+        pass
     by_stage = {"mid_scan": rl_mid, "raw_scan": rl_raw, "clean": rl_clean, "kmer": rl_kmer}
     dominant = max(by_stage, key=lambda k: by_stage[k]["ms"])
     roofline = by_stage[dominant]
@@ -508,7 +573,15 @@ def main():
                    "l2": "inputs (2 B/base, >= 0.5 GB per launch) are larger than the 126 MB L2",
                    "timing": "CUDA events on the library stream around the K1..K5 sequence, max over ranks"},
         "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(2 * n_bases + 8 * (n_reads + len(sub))) * world,
-                "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2},
+                "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2,
+                "input_format": "byte bases + Phred bytes + offsets in pinned host memory (tgsf_submit)"},
+        "e2e_packed": {"value": e2e_packed_value, "unit": "Gbases/s",
+                       "h2d_bytes_per_step": int(pk_off[-1] + n_bases + 8 * (n_reads + len(sub))) * world,
+                       "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2,
+                       "input_format": "2-bit packed bases + Phred bytes + offsets in pinned host memory "
+                                       "(tgsf_submit_packed, the path src/TGSFilter.cpp uses); packing is host "
+                                       "parser work outside the timed region",
+                       "host_pack_gbases_per_s_per_thread": pack_gbs},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

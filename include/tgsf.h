@@ -147,6 +147,15 @@ int tgsf_host_free(void *ptr);
  * of the results are enqueued on the slot's stream and the call returns without waiting. */
 int tgsf_submit(tgsf_ctx *ctx, const uint8_t *bases, const uint8_t *quals, const uint64_t *offsets,
                 uint32_t n_reads);
+/* Same, with the bases 2-bit packed on the host (A0 C1 G2 T3; base i in bits 2*(i%4) of byte i/4,
+ * packing runs over the concatenated stream) — 1.25 instead of 2 bytes per base over PCIe.  Every
+ * byte that is not upper-case ACGT is listed in (exc_pos, exc_byte) and patched in on the device,
+ * so the kernels see exactly the bytes the host parsed.  tgsf_pack_bases is the host-side packer
+ * (CPU, allocation-free; returns TGSF_ERR_CAPACITY with *n_exc = required entries). */
+int tgsf_submit_packed(tgsf_ctx *ctx, const uint8_t *packed_bases, const uint8_t *quals, const uint64_t *offsets,
+                       uint32_t n_reads, const uint64_t *exc_pos, const uint8_t *exc_byte, uint64_t n_exc);
+int tgsf_pack_bases(const uint8_t *bases, uint64_t n, uint8_t *packed, uint64_t *exc_pos, uint8_t *exc_byte,
+                    uint64_t exc_cap, uint64_t *n_exc);
 /* Same, with the three arrays already resident in this GPU's memory (device pointers). */
 int tgsf_submit_device(tgsf_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_quals,
                        const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases);

@@ -283,34 +283,53 @@ private:
     size_t pos_ = 0, len_ = 0;
 };
 
-// ---- pinned varlen batch --------------------------------------------------------------------------
+// ---- varlen batch: byte bases stay on the host for record output; what crosses PCIe is the 2-bit
+// packed stream (pinned) + Phred bytes (pinned) + offsets + the exception list ---------------------
 struct Batch {
-    uint8_t *bases = nullptr, *quals = nullptr;
+    std::vector<uint8_t> bases;     // concatenated, host only
+    uint8_t *packed = nullptr, *quals = nullptr; // tgsf_host_alloc'ed
     size_t cap = 0, used = 0;
     std::vector<uint64_t> offsets{0};
     std::vector<string> names;
+    std::vector<uint64_t> exc_pos;
+    std::vector<uint8_t> exc_byte;
     bool reserve(size_t want) {
         if (want <= cap) return true;
         size_t ncap = std::max(want, cap * 2 + (1 << 20));
-        uint8_t *nb = nullptr, *nq = nullptr;
-        if (tgsf_host_alloc((void **)&nb, ncap) != TGSF_OK || tgsf_host_alloc((void **)&nq, ncap) != TGSF_OK) return false;
-        if (used) { memcpy(nb, bases, used); memcpy(nq, quals, used); }
-        tgsf_host_free(bases);
+        uint8_t *np = nullptr, *nq = nullptr;
+        if (tgsf_host_alloc((void **)&np, ncap / 4 + 64) != TGSF_OK || tgsf_host_alloc((void **)&nq, ncap) != TGSF_OK) return false;
+        if (used) memcpy(nq, quals, used);
+        tgsf_host_free(packed);
         tgsf_host_free(quals);
-        bases = nb; quals = nq; cap = ncap;
+        packed = np; quals = nq; cap = ncap;
         return true;
     }
     bool add(const string &name, const string &seq, const string &qual, bool has_qual) {
         if (!reserve(used + seq.size() + 64)) return false;
-        memcpy(bases + used, seq.data(), seq.size());
+        bases.insert(bases.end(), seq.begin(), seq.end());
         if (has_qual) memcpy(quals + used, qual.data(), seq.size());
         used += seq.size();
         offsets.push_back(used);
         names.push_back(name);
         return true;
     }
-    void clear() { used = 0; offsets.assign(1, 0); names.clear(); }
-    void release() { tgsf_host_free(bases); tgsf_host_free(quals); bases = quals = nullptr; cap = 0; }
+    // 2-bit pack the whole concatenated stream (tgsf_pack_bases), growing the exception list on demand
+    bool pack() {
+        uint64_t ne = 0;
+        exc_pos.resize(std::max<size_t>(exc_pos.size(), 1024));
+        exc_byte.resize(exc_pos.size());
+        int rc = tgsf_pack_bases(bases.data(), used, packed, exc_pos.data(), exc_byte.data(), exc_pos.size(), &ne);
+        if (rc == TGSF_ERR_CAPACITY) {
+            exc_pos.resize(ne);
+            exc_byte.resize(ne);
+            rc = tgsf_pack_bases(bases.data(), used, packed, exc_pos.data(), exc_byte.data(), exc_pos.size(), &ne);
+        }
+        n_exc = ne;
+        return rc == TGSF_OK;
+    }
+    uint64_t n_exc = 0;
+    void clear() { used = 0; bases.clear(); offsets.assign(1, 0); names.clear(); }
+    void release() { tgsf_host_free(packed); tgsf_host_free(quals); packed = quals = nullptr; cap = 0; }
     uint32_t n() const { return (uint32_t)names.size(); }
 };
 
@@ -575,7 +594,7 @@ int main(int argc, char **argv) {
             const string &raw = b.names[last];
             const string name = pass >= 2 ? new_seq_name(raw, pass) : raw;
             pass++;
-            const char *s = (const char *)b.bases + b.offsets[last] + p.start;
+            const char *s = (const char *)b.bases.data() + b.offsets[last] + p.start;
             rec.clear();
             if (P.Outfq == 1) {
                 const char *q = (const char *)b.quals + b.offsets[last] + p.start;
@@ -596,7 +615,10 @@ int main(int argc, char **argv) {
     auto submit = [&](int bi) {
         Batch &b = ring[(size_t)bi];
         tgsf_ctx *c = ctx[(size_t)(bi % P.gpus)];
-        if (tgsf_submit(c, b.bases, has_qual ? b.quals : nullptr, b.offsets.data(), b.n()) != TGSF_OK) die_tgsf("tgsf_submit");
+        if (!b.pack()) die_tgsf("tgsf_pack_bases");
+        if (tgsf_submit_packed(c, b.packed, has_qual ? b.quals : nullptr, b.offsets.data(), b.n(), b.exc_pos.data(),
+                               b.exc_byte.data(), b.n_exc) != TGSF_OK)
+            die_tgsf("tgsf_submit_packed");
         inflight.push_back(bi);
         submitted++;
     };

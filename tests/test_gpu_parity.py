@@ -441,3 +441,24 @@ def test_randomised_parameters_vs_oracle(seed):
         kmer=int(rng.choice([5, 11, 15, 16, 21, 31])), min_repeat=int(rng.choice([0, 0, 3, 30])),
         qtype=0 if fasta else 33, discard=bool(rng.random() < 0.3), adapters=ads, max_read_len=10000)
     _compare(params, batch)
+
+
+def test_packed_2bit_submit_is_byte_identical():
+    # lower case, N and IUPAC bytes travel as exceptions; results must equal the byte path / oracle
+    params, batch, exp = golden_lib.load_perread("multiword")
+    o_reads, o_pieces, o_cnt = oracle_lib.run(params, batch)
+    with FilterEngine(params) as eng:
+        pk, pos, val = eng.pack(batch)
+        assert pos.size > 0 and pk.size >= (batch.n_bases + 3) // 4
+        eng.submit_packed(batch, (pk, pos, val))
+        reads, pieces = eng.collect()
+        cnt = eng.counters().flat
+    assert np.array_equal(reads, o_reads) and np.array_equal(pieces, o_pieces) and np.array_equal(cnt, o_cnt)
+    batch2 = synth.make_config(2, 150, max_len=30000)
+    p2 = synth.config_params(2)
+    o2 = oracle_lib.run(p2, batch2)
+    with FilterEngine(p2) as eng:
+        eng.submit_packed(batch2)
+        r2, pc2 = eng.collect()
+        c2 = eng.counters().flat
+    assert np.array_equal(r2, o2[0]) and np.array_equal(pc2, o2[1]) and np.array_equal(c2, o2[2])

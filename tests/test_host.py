@@ -228,3 +228,29 @@ def test_world_size_2_counters_allreduce_equals_single_process():
     params.max_read_len = 8000
     _, _, single = oracle_lib.run(params, batch)
     np.testing.assert_array_equal(merged, single)
+
+
+def test_pack_bases_roundtrip_on_cpu():
+    lib = _capi.load()
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 3, 4, 5, 1000, 4099):
+        b = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+        if n > 10:
+            b[rng.integers(0, n, 7)] = np.frombuffer(b"NacgtRY", dtype=np.uint8)
+        packed = np.zeros((n + 3) // 4 + 1, dtype=np.uint8)
+        pos = np.zeros(16, dtype=np.uint64)
+        val = np.zeros(16, dtype=np.uint8)
+        ne = C.c_uint64(0)
+        rc = lib.tgsf_pack_bases(b.ctypes.data if n else None, n, packed.ctypes.data, pos.ctypes.data,
+                                 val.ctypes.data, 16, C.byref(ne))
+        assert rc == 0
+        codes = (packed[np.arange(n) // 4] >> (2 * (np.arange(n) % 4))) & 3
+        rec = np.frombuffer(b"ACGT", dtype=np.uint8)[codes].copy()
+        rec[pos[:ne.value].astype(np.int64)] = val[:ne.value]
+        assert np.array_equal(rec, b)
+    # capacity error reports the required size
+    b = np.frombuffer(b"NNNNNNNN", dtype=np.uint8).copy()
+    packed = np.zeros(4, dtype=np.uint8)
+    ne = C.c_uint64(0)
+    assert lib.tgsf_pack_bases(b.ctypes.data, 8, packed.ctypes.data, None, None, 0, C.byref(ne)) == _capi.TGSF_ERR_CAPACITY
+    assert ne.value == 8

@@ -111,7 +111,7 @@ ALIGN_RESULT_DTYPE = [("edit_distance", "<i4"), ("n_locations", "<i4"), ("align_
 # every symbol include/tgsf.h declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
     "tgsf_version", "tgsf_last_error", "tgsf_create", "tgsf_destroy", "tgsf_host_alloc",
-    "tgsf_host_free", "tgsf_submit", "tgsf_submit_device", "tgsf_collect", "tgsf_last_timing", "tgsf_last_stage_ms",
+    "tgsf_host_free", "tgsf_submit", "tgsf_submit_packed", "tgsf_pack_bases", "tgsf_submit_device", "tgsf_collect", "tgsf_last_timing", "tgsf_last_stage_ms",
     "tgsf_counter_layout_get", "tgsf_counters", "tgsf_counters_reset", "tgsf_counters_device",
     "tgsf_launch_count", "tgsf_allreduce", "tgsf_prepass", "tgsf_align_hw",
 )
@@ -139,6 +139,8 @@ def load() -> C.CDLL:
     lib.tgsf_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.tgsf_host_free.argtypes = [vp]
     lib.tgsf_submit.argtypes = [vp, u8p, u8p, u64p, C.c_uint32]
+    lib.tgsf_submit_packed.argtypes = [vp, u8p, u8p, u64p, C.c_uint32, u64p, u8p, C.c_uint64]
+    lib.tgsf_pack_bases.argtypes = [u8p, C.c_uint64, u8p, u64p, u8p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.tgsf_submit_device.argtypes = [vp, u8p, u8p, u64p, C.c_uint32, C.c_uint64]
     lib.tgsf_collect.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.tgsf_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]

@@ -71,8 +71,26 @@ static __device__ void mid_chunk_record(const u64 *__restrict__ tab, int tab_str
     }
 }
 
+// Rare path of k_mid_scan: exact column-by-column minimum of one 8-column group, replayed from
+// the state saved at the group start.  Kept out of line so that it costs the hot loop no registers.
+template <int NW>
+static __device__ __noinline__ int mid_replay_group(const u64 *P0, const u64 *M0, u32 w0, u32 w1,
+                                                    const u64 *tab, int tab_stride, int best) {
+    u64 tP[NW], tM[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { tP[w] = P0[w]; tM[w] = M0[w]; }
+    const u32 wd[2] = {w0, w1};
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) {
+        const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        myers_step_state<NW>(tP, tM, tab + byte * tab_stride);
+        best = min(best, myers_score<NW>(tP, tM));
+    }
+    return best;
+}
+
 template <int NW, int AP>
-__global__ void __launch_bounds__(MID_THREADS)
+__global__ void __launch_bounds__(MID_THREADS, (NW * AP <= 2) ? 6 : 3)
 k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__restrict__ chunks,
                const u32 *__restrict__ perm, const u32 *__restrict__ n_chunks_ptr,
                uint8_t *__restrict__ chunk_min,
@@ -114,7 +132,6 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
 
         u64 Pv[AP][NW], Mv[AP][NW];
         int score[AP], best[AP];
-        u32 hP[AP], hM[AP];
         bool on[AP];
 #pragma unroll
         for (int x = 0; x < AP; ++x) {
@@ -124,7 +141,6 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
             for (int w = 0; w < NW; ++w) { Pv[x][w] = s0.Pv[w]; Mv[x][w] = s0.Mv[w]; }
             score[x] = A[x].qlen;
             best[x] = 0x7fffffff;
-            hP[x] = hM[x] = 0;
             on[x] = A[x].k_mid > 0 && tsm >= (i64)A[x].qlen; // tsmLen >= qLen, T.cpp:1237
         }
         if (tsm >= (i64)qmin) {
@@ -134,8 +150,8 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
                 const u64 *eq = s_peq + (u32)B.bases[p] * TS;
 #pragma unroll
                 for (int x = 0; x < AP; ++x) {
-                    myers_step_hist<NW>(Pv[x], Mv[x], eq + x * NW, hP[x], hM[x]);
-                    score[x] += (int)(hP[x] & 1u) - (int)(hM[x] & 1u);
+                    myers_step_state<NW>(Pv[x], Mv[x], eq + x * NW);
+                    score[x] = myers_score<NW>(Pv[x], Mv[x]);
                     if (p >= ob) best[x] = min(best[x], score[x]);
                 }
                 ++p;
@@ -144,25 +160,36 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
             for (; p + 16 <= oe; p += 16) {
                 const uint4 v = __ldg(b16 + (p >> 4));
                 const u32 wd[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
-                    const u64 *eq = s_peq + byte * TS;
-#pragma unroll
-                    for (int x = 0; x < AP; ++x) myers_step_hist<NW>(Pv[x], Mv[x], eq + x * NW, hP[x], hM[x]);
-                }
                 const bool tracked = p >= ob;
 #pragma unroll
-                for (int x = 0; x < AP; ++x) {
-                    const u32 plus = hP[x] & 0xffffu, minus = hM[x] & 0xffffu;
-                    if (tracked && score[x] - __popc(minus) <= min(A[x].k_mid, best[x] - 1)) {
-                        int sc = score[x];
-                        for (int j = 15; j >= 0; --j) { // oldest column first
-                            sc += (int)((plus >> j) & 1u) - (int)((minus >> j) & 1u);
-                            best[x] = min(best[x], sc);
+                for (int h = 0; h < 2; ++h) { // two 8-column groups per 16-byte load
+                    u64 Pv0[AP][NW], Mv0[AP][NW]; // state at the group start (only read on the rare path)
+#pragma unroll
+                    for (int x = 0; x < AP; ++x)
+#pragma unroll
+                        for (int w = 0; w < NW; ++w) { Pv0[x][w] = Pv[x][w]; Mv0[x][w] = Mv[x][w]; }
+#pragma unroll
+                    for (int j = 8 * h; j < 8 * h + 8; ++j) {
+                        const u32 byte = (wd[j >> 2] >> (8 * (j & 3))) & 0xffu;
+                        const u64 *eq = s_peq + byte * TS;
+#pragma unroll
+                        for (int x = 0; x < AP; ++x) myers_step_state<NW>(Pv[x], Mv[x], eq + x * NW);
+                    }
+                    if (tracked) {
+#pragma unroll
+                        for (int x = 0; x < AP; ++x) {
+                            const int s_end = myers_score<NW>(Pv[x], Mv[x]);
+                            // adjacent columns differ by at most 1: group minimum >= (s_0 + s_8 - 8) / 2
+                            if (((score[x] + s_end - 8 + 1) >> 1) <= min(A[x].k_mid, best[x] - 1))
+                                best[x] = mid_replay_group<NW>(Pv0[x], Mv0[x], wd[2 * h], wd[2 * h + 1],
+                                                               s_peq + x * NW, TS, best[x]);
+                            score[x] = s_end;
                         }
                     }
-                    score[x] += __popc(plus) - __popc(minus);
+                }
+                if (!tracked && p + 16 >= ob) { // last halo group: the first tracked group needs s_0
+#pragma unroll
+                    for (int x = 0; x < AP; ++x) score[x] = myers_score<NW>(Pv[x], Mv[x]);
                 }
             }
             // tail
@@ -170,8 +197,8 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
                 const u64 *eq = s_peq + (u32)B.bases[p] * TS;
 #pragma unroll
                 for (int x = 0; x < AP; ++x) {
-                    myers_step_hist<NW>(Pv[x], Mv[x], eq + x * NW, hP[x], hM[x]);
-                    score[x] += (int)(hP[x] & 1u) - (int)(hM[x] & 1u);
+                    myers_step_state<NW>(Pv[x], Mv[x], eq + x * NW);
+                    score[x] = myers_score<NW>(Pv[x], Mv[x]);
                     if (p >= ob) best[x] = min(best[x], score[x]);
                 }
             }

@@ -84,12 +84,13 @@ static __device__ __forceinline__ void myers_step(Myers<NW> &s, const u64 *__res
     }
 }
 
-// HW column for the hot scan loop: no score register; the horizontal delta of the query's bottom
-// row (bit 63 of the last word of Ph / Mh) is shifted into two 32-bit histories instead, which the
-// caller folds into the score once per 16 columns (exact: see k_mid_scan).
-template <int NW>
-static __device__ __forceinline__ void myers_step_hist(u64 (&sPv)[NW], u64 (&sMv)[NW],
-                                                       const u64 *__restrict__ eq, u32 &hP, u32 &hM) {
+// HW column for the hot scan loop: state only.  The bottom-row score is never carried along: in the
+// top-padded HW layout the top boundary is 0 and the wildcard rows have zero vertical deltas, so
+// H[q][j] = popc(Pv_j) - popc(Mv_j) can be read off the state whenever it is needed
+// (myers_score); k_mid_scan does that once per 16 columns.
+template <int NW, bool HIST = false>
+static __device__ __forceinline__ void myers_step_state(u64 (&sPv)[NW], u64 (&sMv)[NW],
+                                                        const u64 *__restrict__ eq, u32 *hM = nullptr) {
     int hin = 0;
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
@@ -101,10 +102,8 @@ static __device__ __forceinline__ void myers_step_hist(u64 (&sPv)[NW], u64 (&sMv
         const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
         u64 Ph = Mv | ~(Xh | Pv);
         u64 Mh = Pv & Xh;
-        if (w == NW - 1) {
-            hP = __funnelshift_l((u32)(Ph >> 32), hP, 1);
-            hM = __funnelshift_l((u32)(Mh >> 32), hM, 1);
-        }
+        // optional history of the bottom row's -1 steps (bit 63 of the last word of Mh)
+        if (HIST && w == NW - 1) *hM = __funnelshift_l((u32)(Mh >> 32), *hM, 1);
         const int hout = (w == NW - 1) ? 0 : (int)(Ph >> 63) - (int)(Mh >> 63);
         Ph <<= 1;
         Mh <<= 1;
@@ -117,12 +116,20 @@ static __device__ __forceinline__ void myers_step_hist(u64 (&sPv)[NW], u64 (&sMv
         hin = hout;
     }
 }
+template <int NW>
+static __device__ __forceinline__ int myers_score(const u64 (&Pv)[NW], const u64 (&Mv)[NW]) {
+    int s = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) s += __popcll(Pv[w]) - __popcll(Mv[w]);
+    return s;
+}
 
 // Measured and rejected (round 1): moving the 64-bit add and the two 1-bit shifts onto the FMA pipe
 // with mad.wide.u32 (IMAD.WIDE) made k_mid_scan 21 % slower (12.0 -> 14.6 ms on config[1]): ALU-pipe
 // instructions fell from 20.2 to 17.5 per column but IMAD.WIDE.U32 issues at about a quarter of the
 // IMAD rate, so the FMA pipe became the limiter.  The plain C form below already compiles to the
 // 32-bit IADD3 + IMAD.X pairs that split each add/shift one ALU op + one FMA op.
+// Also replaced (round 1): per-column Ph/Mh top-bit histories (2 SHF per column) by myers_score.
 
 // Bounds on the match count of ANY optimal global alignment of a q-long query against a tl-long
 // target with edit distance d: with X mismatches, I insertions, D deletions and M matches,

@@ -190,7 +190,7 @@ struct Slot {
     cudaEvent_t ev_stage[TGSF_N_STAGES + 1] = {};
     bool busy = false;
     // input
-    DBuf in_bases, in_quals, in_offsets;
+    DBuf in_bases, in_quals, in_offsets, in_packed, in_exc_pos, in_exc_val;
     DevBatch B{};
     u64 n_bases = 0;
     bool has_qual = false;
@@ -261,7 +261,7 @@ int slot_init(Slot &s) {
 }
 
 void slot_release(Slot &s) {
-    DBuf *bufs[] = {&s.in_bases, &s.in_quals, &s.in_offsets, &s.seg_start, &s.seg_len, &s.seg_sum,
+    DBuf *bufs[] = {&s.in_bases, &s.in_quals, &s.in_offsets, &s.in_packed, &s.in_exc_pos, &s.in_exc_val, &s.seg_start, &s.seg_len, &s.seg_sum,
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
                     &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
@@ -469,16 +469,16 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                 M.n_adapters = A;
                 TRY(for_nw(nw, [&](auto nwc) {
                     constexpr int NW = decltype(nwc)::value;
-                    if (pair)
-                        k_mid_scan_dyn<NW, 2><<<c->sm_count * 8, MID_THREADS, 256 * 2 * NW * sizeof(u64), st>>>(
+                    auto launch = [&](auto kern, size_t smem) {
+                        int occ = 0; // persistent grid: exactly the resident CTA count
+                        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MID_THREADS, smem) != cudaSuccess || occ < 1) occ = 4;
+                        kern<<<c->sm_count * occ, MID_THREADS, smem, st>>>(
                             s.B, AC, M, s.chunks.as<ChunkEntry>(), s.chunk_perm.as<u32>(), n_chunks_ptr,
                             s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
                             s.best_mid.as<u32>());
-                    else
-                        k_mid_scan_dyn<NW, 1><<<c->sm_count * 8, MID_THREADS, 256 * NW * sizeof(u64), st>>>(
-                            s.B, AC, M, s.chunks.as<ChunkEntry>(), s.chunk_perm.as<u32>(), n_chunks_ptr,
-                            s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
-                            s.best_mid.as<u32>());
+                    };
+                    if (pair) launch(k_mid_scan_dyn<NW, 2>, 256 * 2 * NW * sizeof(u64));
+                    else launch(k_mid_scan_dyn<NW, 1>, 256 * NW * sizeof(u64));
                     c->launches++;
                     return check_launch("k_mid_scan");
                 }));
@@ -752,10 +752,17 @@ int tgsf_host_free(void *ptr) {
     return TGSF_OK;
 }
 
+struct PackedIn { // optional 2-bit input of tgsf_submit_packed
+    const uint8_t *packed = nullptr;
+    const u64 *exc_pos = nullptr;
+    const uint8_t *exc_val = nullptr;
+    u64 n_exc = 0;
+};
+
 static int submit_common(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals, const u64 *offsets,
-                         u32 n_reads, u64 n_bases, bool on_device) {
+                         u32 n_reads, u64 n_bases, bool on_device, const PackedIn *pk = nullptr) {
     if (!c) { set_err("ctx is NULL"); return TGSF_ERR_INVALID; }
-    if (n_reads && (!bases || !offsets)) { set_err("bases/offsets NULL"); return TGSF_ERR_INVALID; }
+    if (n_reads && ((!bases && !pk) || !offsets)) { set_err("bases/offsets NULL"); return TGSF_ERR_INVALID; }
     if (n_reads > (1u << 24)) { set_err("more than 2^24 reads in one batch"); return TGSF_ERR_INVALID; }
     if (c->outstanding == c->slots.size()) { set_err("all %zu slots busy: collect first", c->slots.size()); return TGSF_ERR_STATE; }
     CU(cudaSetDevice(c->device));
@@ -773,7 +780,27 @@ static int submit_common(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals
         const size_t pad = 64;
         TRY(s.in_bases.ensure((size_t)n_bases + pad));
         TRY(s.in_offsets.ensure(((size_t)n_reads + 1) * sizeof(u64)));
-        if (n_bases) CU(cudaMemcpyAsync(s.in_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, s.stream));
+        if (pk) {
+            const u64 n_words = (n_bases + 15) / 16; // u32 words of packed input = 16 bases each
+            TRY(s.in_bases.ensure((size_t)n_words * 16 + pad));
+            TRY(s.in_packed.ensure((size_t)n_words * 4 + pad));
+            if (n_bases) {
+                CU(cudaMemcpyAsync(s.in_packed.p, pk->packed, (size_t)((n_bases + 3) / 4), cudaMemcpyHostToDevice, s.stream));
+                k_unpack_bases<<<c->sm_count * 8, 256, 0, s.stream>>>(s.in_packed.as<u32>(), n_words, s.in_bases.as<uint4>());
+                c->launches++;
+            }
+            if (pk->n_exc) {
+                TRY(s.in_exc_pos.ensure((size_t)pk->n_exc * sizeof(u64)));
+                TRY(s.in_exc_val.ensure((size_t)pk->n_exc));
+                CU(cudaMemcpyAsync(s.in_exc_pos.p, pk->exc_pos, (size_t)pk->n_exc * sizeof(u64), cudaMemcpyHostToDevice, s.stream));
+                CU(cudaMemcpyAsync(s.in_exc_val.p, pk->exc_val, (size_t)pk->n_exc, cudaMemcpyHostToDevice, s.stream));
+                k_apply_exceptions<<<c->sm_count, 256, 0, s.stream>>>(s.in_bases.as<uint8_t>(), s.in_exc_pos.as<u64>(),
+                                                                     s.in_exc_val.as<uint8_t>(), pk->n_exc);
+                c->launches++;
+            }
+        } else if (n_bases) {
+            CU(cudaMemcpyAsync(s.in_bases.p, bases, (size_t)n_bases, cudaMemcpyHostToDevice, s.stream));
+        }
         if (quals) {
             TRY(s.in_quals.ensure((size_t)n_bases + pad));
             if (n_bases) CU(cudaMemcpyAsync(s.in_quals.p, quals, (size_t)n_bases, cudaMemcpyHostToDevice, s.stream));
@@ -796,6 +823,64 @@ int tgsf_submit(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals, const u
     if (n_reads && !offsets) { set_err("offsets NULL"); return TGSF_ERR_INVALID; }
     const u64 n_bases = n_reads ? offsets[n_reads] : 0;
     return submit_common(c, bases, quals, (const u64 *)offsets, n_reads, n_bases, false);
+}
+
+int tgsf_submit_packed(tgsf_ctx *c, const uint8_t *packed_bases, const uint8_t *quals, const uint64_t *offsets,
+                       uint32_t n_reads, const uint64_t *exc_pos, const uint8_t *exc_byte, uint64_t n_exc) {
+    if (n_reads && (!offsets || !packed_bases)) { set_err("packed/offsets NULL"); return TGSF_ERR_INVALID; }
+    if (n_exc && (!exc_pos || !exc_byte)) { set_err("exception arrays NULL"); return TGSF_ERR_INVALID; }
+    const u64 n_bases = n_reads ? offsets[n_reads] : 0;
+    for (u64 i = 0; i < n_exc; ++i)
+        if (exc_pos[i] >= n_bases) { set_err("exception position out of range"); return TGSF_ERR_INVALID; }
+    PackedIn pk;
+    pk.packed = packed_bases;
+    pk.exc_pos = (const u64 *)exc_pos;
+    pk.exc_val = exc_byte;
+    pk.n_exc = n_exc;
+    return submit_common(c, nullptr, quals, (const u64 *)offsets, n_reads, n_bases, false, &pk);
+}
+
+int tgsf_pack_bases(const uint8_t *bases, uint64_t n, uint8_t *packed, uint64_t *exc_pos, uint8_t *exc_byte,
+                    uint64_t exc_cap, uint64_t *n_exc) {
+    if ((n && (!bases || !packed)) || !n_exc) { set_err("pack: NULL argument"); return TGSF_ERR_INVALID; }
+    static const struct Lut { uint8_t code[256]; Lut() { memset(code, 4, 256); code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3; } } lut;
+    u64 ne = 0;
+    const u64 full = n / 4;
+    for (u64 i = 0; i < full; ++i) {
+        const uint8_t c0 = lut.code[bases[4 * i]], c1 = lut.code[bases[4 * i + 1]], c2 = lut.code[bases[4 * i + 2]],
+                      c3 = lut.code[bases[4 * i + 3]];
+        if ((c0 | c1 | c2 | c3) & 4) { // rare: at least one byte is not upper-case ACGT
+            uint8_t v = 0;
+            for (int j = 0; j < 4; ++j) {
+                const uint8_t cj = lut.code[bases[4 * i + j]];
+                if (cj & 4) {
+                    if (exc_pos && ne < exc_cap) { exc_pos[ne] = 4 * i + j; exc_byte[ne] = bases[4 * i + j]; }
+                    ++ne;
+                } else {
+                    v |= (uint8_t)(cj << (2 * j));
+                }
+            }
+            packed[i] = v;
+        } else {
+            packed[i] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
+        }
+    }
+    if (n & 3) {
+        uint8_t v = 0;
+        for (u64 j = 0; j < (n & 3); ++j) {
+            const uint8_t cj = lut.code[bases[4 * full + j]];
+            if (cj & 4) {
+                if (exc_pos && ne < exc_cap) { exc_pos[ne] = 4 * full + j; exc_byte[ne] = bases[4 * full + j]; }
+                ++ne;
+            } else {
+                v |= (uint8_t)(cj << (2 * j));
+            }
+        }
+        packed[full] = v;
+    }
+    *n_exc = ne;
+    if (ne > exc_cap) { set_err("pack: %llu exceptions, capacity %llu", (unsigned long long)ne, (unsigned long long)exc_cap); return TGSF_ERR_CAPACITY; }
+    return TGSF_OK;
 }
 
 int tgsf_submit_device(tgsf_ctx *c, const uint8_t *d_bases, const uint8_t *d_quals, const uint64_t *d_offsets,

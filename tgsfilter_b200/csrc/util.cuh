@@ -206,3 +206,28 @@ __global__ void k_check_pool(const u32 *__restrict__ pool_total, u32 pool_cap,
 __global__ void k_add_u64(u64 *__restrict__ dst, const u64 *__restrict__ src, u32 n) {
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
 }
+
+// 2-bit packed bases (A0 C1 G2 T3, base i in bits 2*(i%4) of byte i/4) -> ASCII bytes.  One thread
+// expands 4 packed bytes into one 16-byte store.  Bytes that are not upper-case ACGT travel as an
+// exception list and are patched in afterwards, so the reconstructed stream is byte-identical to
+// what the host parsed (edlib compares raw bytes, the QC counts fold case: SURVEY.md D5).
+__global__ void k_unpack_bases(const u32 *__restrict__ packed, u64 n_words, uint4 *__restrict__ out) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (u64)gridDim.x * blockDim.x) {
+        const u32 w = packed[i];
+        u32 o[4];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const u32 byte = (w >> (8 * b)) & 0xffu;
+            // selector nibbles = the four 2-bit codes; table bytes = 'A','C','G','T'
+            const u32 sel = (byte & 3u) | ((byte & 0xcu) << 2) | ((byte & 0x30u) << 4) | ((byte & 0xc0u) << 6);
+            o[b] = __byte_perm(0x54474341u, 0u, sel);
+        }
+        out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__global__ void k_apply_exceptions(uint8_t *__restrict__ bases, const u64 *__restrict__ pos,
+                                   const uint8_t *__restrict__ val, u64 n) {
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64)gridDim.x * blockDim.x)
+        bases[pos[i]] = val[i];
+}

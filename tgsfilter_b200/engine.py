@@ -85,6 +85,44 @@ class FilterEngine:
             offs.ctypes.data, n), "tgsf_submit")
         self._inflight.append((n, (bases, quals, offs)))
 
+    def pack(self, batch):
+        """tgsf_pack_bases on a ReadBatch: returns (packed, exc_pos, exc_byte) numpy arrays."""
+        bases = np.ascontiguousarray(batch.bases, dtype=np.uint8)
+        n = bases.size
+        packed = np.zeros((n + 3) // 4 + 16, dtype=np.uint8)
+        cap = 1024
+        while True:
+            pos = np.zeros(cap, dtype=np.uint64)
+            val = np.zeros(cap, dtype=np.uint8)
+            ne = C.c_uint64(0)
+            rc = self._lib.tgsf_pack_bases(bases.ctypes.data if n else None, n, packed.ctypes.data,
+                                           pos.ctypes.data, val.ctypes.data, cap, C.byref(ne))
+            if rc == _capi.TGSF_ERR_CAPACITY:
+                cap = int(ne.value)
+                continue
+            _capi.check(rc, "tgsf_pack_bases")
+            return packed, pos[:ne.value], val[:ne.value]
+
+    def submit_packed(self, batch, packed=None) -> None:
+        """2-bit packed bases over PCIe (tgsf_submit_packed)."""
+        if packed is None:
+            packed = self.pack(batch)
+        pk, pos, val = packed
+        quals = None if batch.quals is None else np.ascontiguousarray(batch.quals, dtype=np.uint8)
+        offs = np.ascontiguousarray(batch.offsets, dtype=np.uint64)
+        n = len(offs) - 1
+        _capi.check(self._lib.tgsf_submit_packed(
+            self._ctx, pk.ctypes.data, None if quals is None else quals.ctypes.data, offs.ctypes.data, n,
+            pos.ctypes.data if pos.size else None, val.ctypes.data if val.size else None, pos.size),
+            "tgsf_submit_packed")
+        self._inflight.append((n, (pk, pos, val, quals, offs)))
+
+    def submit_packed_raw(self, packed_ptr: int, quals_ptr, offsets_ptr: int, n_reads: int,
+                          exc_pos_ptr=None, exc_byte_ptr=None, n_exc: int = 0, keep=None) -> None:
+        _capi.check(self._lib.tgsf_submit_packed(self._ctx, packed_ptr, quals_ptr, offsets_ptr, n_reads,
+                                                 exc_pos_ptr, exc_byte_ptr, n_exc), "tgsf_submit_packed")
+        self._inflight.append((n_reads, keep))
+
     def submit_raw(self, bases_ptr: int, quals_ptr: Optional[int], offsets_ptr: int, n_reads: int,
                    keep=None) -> None:
         """Host pointers (e.g. pinned torch tensors' data_ptr())."""
