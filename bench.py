@@ -11,8 +11,10 @@ auto-identify + end trim); every rank of a multi-GPU run processes its own shard
 after the timed region).
 
 `value`  : input bases / device time, inputs resident in HBM (CUDA events on the library's stream)
-`e2e`    : same metric through tgsf_submit with pinned HOST buffers, H2D + kernels + D2H of the
-           results inside the timed region
+`e2e`    : same metric through the C-ABI with pinned HOST buffers, H2D + kernels + D2H of the results
+           inside the timed region, in the input format the C++ host (src/TGSFilter.cpp) feeds:
+           2-bit packed bases + Phred bytes (tgsf_submit_packed); `e2e_bytes` is the same through
+           tgsf_submit with one byte per base.  Both are PCIe-bound.
 `roofline`: dominant kernel (K3 k_mid_scan, INT-ALU bound per SURVEY.md §8(d)); the HBM-bound K1
            scan is reported next to it under `roofline_kernels`
 `cpu_baseline`: the UNMODIFIED reference CLI (oracle/_ref/tgsfilter) on a bounded sample of the
@@ -535,7 +537,8 @@ def main():
                 "peak": hbm_peak, "unit": "GB/s", "frac": clean_gbs / hbm_peak, "traffic": None,
                 "peak_source": hbm_src, "work": "2 B per kept base (upper bound: bases of reads passing -q/-Q)",
                 "ms": clean_ms, "share_of_step": clean_ms / step_ms if step_ms else None}
-    rl_kmer = {"kernel": "k_kmer (K4 shared-memory hash set)", "bound": "smem_atomics",
+    rl_kmer = {"kernel": "k_kmer_bitmap (K4, L2-resident 4^k-bit map per CTA; k > 13: shared-memory hash)",
+               "bound": "l2_atomics (one scattered atomicOr + one scattered clear per k-mer: L1tex wavefront rate)",
                "achieved": kept_bases / (kmer_ms / 1e3) / 1e9 if kmer_ms > 0 else 0.0, "peak": None,
                "unit": "Ginserts/s", "frac": None, "traffic": None, "work": "1 insert per kept base",
                "ms": kmer_ms, "share_of_step": kmer_ms / step_ms if step_ms else None}
@@ -572,10 +575,10 @@ def main():
                    "head_trim": params.head_trim, "tail_trim": params.tail_trim,
                    "l2": "inputs (2 B/base, >= 0.5 GB per launch) are larger than the 126 MB L2",
                    "timing": "CUDA events on the library stream around the K1..K5 sequence, max over ranks"},
-        "e2e": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(2 * n_bases + 8 * (n_reads + len(sub))) * world,
+        "e2e_bytes": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(2 * n_bases + 8 * (n_reads + len(sub))) * world,
                 "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2,
                 "input_format": "byte bases + Phred bytes + offsets in pinned host memory (tgsf_submit)"},
-        "e2e_packed": {"value": e2e_packed_value, "unit": "Gbases/s",
+        "e2e": {"value": e2e_packed_value, "unit": "Gbases/s",
                        "h2d_bytes_per_step": int(pk_off[-1] + n_bases + 8 * (n_reads + len(sub))) * world,
                        "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2,
                        "input_format": "2-bit packed bases + Phred bytes + offsets in pinned host memory "

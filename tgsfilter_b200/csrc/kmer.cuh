@@ -91,3 +91,70 @@ k_kmer(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pi
         }
     }
 }
+
+// k <= 13: direct-addressed bitmap of the 4^k key space in global memory, one per CTA (512 KB for
+// k = 11, so the bitmaps of all 148 CTAs stay L2-resident).  One atomicOr per k-mer (its return value
+// tells whether the k-mer is new), then the touched words are zeroed again with plain stores, so
+// the bitmap is clean for the CTA's next piece without a 512 KB memset per read.  Replaces the
+// shared-memory hash for small k: no probing, no passes, and L2 atomics issue ~1.5x faster per SM
+// than shared-memory CAS.
+#define KMER_BM_THREADS 512
+__global__ void __launch_bounds__(KMER_BM_THREADS)
+k_kmer_bitmap(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pieces_ptr,
+              u32 *__restrict__ bitmaps, u64 words_per_cta, u64 *__restrict__ counters,
+              const u32 *__restrict__ dev_status) {
+    if (*dev_status != DEV_STATUS_OK) return;
+    __shared__ u32 s_distinct;
+    u32 *bm = bitmaps + (u64)blockIdx.x * words_per_cta;
+    const int k = P.kmer;
+    const u32 mask = (u32)((1ull << (2 * k)) - 1ull);
+    const u32 n_pieces = *n_pieces_ptr;
+    for (u32 pi = blockIdx.x; pi < n_pieces; pi += gridDim.x) {
+        tgsf_piece pc = pieces[pi];
+        if (pc.status != TGSF_PIECE_EMIT) continue;
+        const int L = pc.len;
+        const int total = L - k + 1;
+        int repeat;
+        if (total <= 0) {
+            repeat = total - 1;
+        } else {
+            const uint8_t *seq = B.bases + B.offsets[pc.read] + (u64)pc.start;
+            if (threadIdx.x == 0) s_distinct = 0;
+            __syncthreads();
+            const int per = (total + KMER_BM_THREADS - 1) / KMER_BM_THREADS;
+            const int i0 = min((int)threadIdx.x * per, total), i1 = min(i0 + per, total);
+            u32 mine = 0;
+            if (i0 < i1) {
+                u32 km = 0;
+                for (int j = 0; j < k - 1; ++j) km = (km << 2) | base_code(seq[i0 + j]);
+                for (int i = i0; i < i1; ++i) {
+                    km = ((km << 2) | base_code(seq[i + k - 1])) & mask;
+                    const u32 bit = 1u << (km & 31u);
+                    const u32 old = atomicOr(bm + (km >> 5), bit);
+                    mine += (old & bit) ? 0u : 1u;
+                }
+            }
+            atomicAdd(&s_distinct, mine);
+            __syncthreads();
+            repeat = total - (int)s_distinct;
+            if (i0 < i1) { // wipe exactly the words this piece touched
+                u32 km = 0;
+                for (int j = 0; j < k - 1; ++j) km = (km << 2) | base_code(seq[i0 + j]);
+                for (int i = i0; i < i1; ++i) {
+                    km = ((km << 2) | base_code(seq[i + k - 1])) & mask;
+                    bm[km >> 5] = 0u;
+                }
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            pc.repeat_len = repeat;
+            if (repeat < P.min_repeat) { // T.cpp:1984-1988
+                pc.status = TGSF_PIECE_SHORT_REPEAT;
+                atomic_add_u64(counters + P.L.drop_info + 15, 1ull);
+                atomic_add_u64(counters + P.L.drop_info + 16, (u64)pc.len);
+            }
+            pieces[pi] = pc;
+        }
+    }
+}

@@ -199,7 +199,7 @@ struct Slot {
     DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first, chunk_perm, chunk_hist;
     int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
-    DBuf scan_tmp;
+    DBuf scan_tmp, kmer_bitmaps;
     Scratch scratch;
     u32 pool_cap = 0, pieces_cap = 0, chunks_cap = 0, tiles_cap = 0;
     // host results
@@ -265,7 +265,7 @@ void slot_release(Slot &s) {
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
                     &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
-                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.scratch.buf};
+                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.scratch.buf};
     for (DBuf *b : bufs) b->release();
     s.h_res.release();
     s.h_pieces.release();
@@ -566,7 +566,19 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
     c->launches++;
     CU(cudaEventRecord(s.ev_stage[5], st));
     if (!(P.flags & TGSF_FLAG_ONLY_QC)) {
-        if (P.min_repeat > 0) {
+        if (P.min_repeat > 0 && P.kmer <= 13) {
+            // bitmap path: one 4^k-bit map per CTA, zeroed once and kept clean by the kernel
+            const u64 words = (1ull << (2 * P.kmer)) / 32 + 1;
+            const int grid = P.kmer <= 11 ? c->sm_count : std::max(1, c->sm_count / (1 << (2 * (P.kmer - 11))));
+            const size_t bytes = (size_t)grid * words * sizeof(u32);
+            if (s.kmer_bitmaps.cap < bytes) {
+                TRY(s.kmer_bitmaps.ensure(bytes));
+                CU(cudaMemsetAsync(s.kmer_bitmaps.p, 0, s.kmer_bitmaps.cap, st));
+            }
+            k_kmer_bitmap<<<grid, KMER_BM_THREADS, 0, st>>>(s.B, P, s.pieces.as<tgsf_piece>(), &H->tmp_cursor,
+                                                            s.kmer_bitmaps.as<u32>(), words, C, &H->status);
+            c->launches++;
+        } else if (P.min_repeat > 0) {
             if (P.kmer <= 15)
                 k_kmer<u32><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
                                                                             &H->tmp_cursor, C, &H->status);
