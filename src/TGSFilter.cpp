@@ -10,8 +10,9 @@
 // replaced by: parse -> pinned varlen batches -> tgsf_submit (async, two batches in flight per GPU,
 // batches dealt round-robin over the GPUs) -> tgsf_collect -> records in input order (= -t 1).
 //
-// Not in this host (SURVEY.md §8(f) "next"): BAM/SAM input (needs htslib), the HTML report, the
-// downsampling second pass.  They are rejected with a clear message, never silently skipped.
+// Downsampling (-g/-d/-r/-R, -F) follows DownSampleTask's selection (T.cpp:2297-2344) over the
+// filtered records.  Not in this host (SURVEY.md §8(f) "next"): BAM/SAM input (needs htslib) and
+// the HTML report; BAM is rejected with a clear message, never silently skipped.
 #include <zlib.h>
 
 #include <algorithm>
@@ -89,7 +90,12 @@ int usage() {
                  "   -s  <float>  min similarity for end adapter\n"
                  "   -S  <float>  min similarity for middle adapter\n"
                  "   -D           discard reads with middle adapter instead of split\n"
-                 " Downsampling options (-g -d -r -R -F): not available in this GPU host\n"
+                 " Downsampling options:\n"
+                 "   -g   <str>   genome size (k/m/g)\n"
+                 "   -d   <int>   downsample to the desired coverage (requires -g) \n"
+                 "   -r   <int>   downsample to the desired number of reads \n"
+                 "   -R  <float>  downsample to the desired fraction of reads \n"
+                 "   -F           disable reads filter, only for downsampling\n"
                  "   -k   <int>   kmer size for repeat evaluations [11] \n"
                  "   -p   <int>   min repeat length of reads [0] \n"
                  " Other options:\n"
@@ -184,12 +190,14 @@ int parse_cmd(int argc, char **argv, Params *P) {
         cerr << "INFO: min similarity for middle adapter: " << P->MidSim << endl;
         cerr << "INFO: min similarity for end adapter: " << P->EndSim << endl;
     }
-    if (P->DesiredNum > 0 || P->DesiredFrac > 0 || P->GenomeSize > 0 || P->DesiredDepth > 0) P->Downsample = true;
-    if (P->Downsample) {
-        cerr << "Error: downsampling (-g/-d/-r/-R) is not available in this GPU host; run the filter first." << endl;
-        exit(-1);
+    if (P->DesiredNum > 0 || P->DesiredFrac > 0) { // T.cpp:463-480
+        P->Downsample = true;
+    } else if (P->GenomeSize > 0 || P->DesiredDepth > 0) {
+        if (P->GenomeSize > 0 && P->DesiredDepth > 0) P->Downsample = true;
+        else if (P->GenomeSize > 0) { cerr << "Error: The desired depth was required, along with the genome size!" << endl; exit(-1); }
+        else { cerr << "Error: The genome size was required, along with the desired depth!" << endl; exit(-1); }
     }
-    if (!P->Filter && !P->OnlyQC) {
+    if (!P->Filter && !P->Downsample && !P->OnlyQC) {
         cerr << "Error: Please set functional parameters for filter, downsampling or quality control." << endl;
         exit(-1);
     }
@@ -391,6 +399,50 @@ int base_content_trim(const std::vector<int32_t> &bn, int checkLen, int seqNum, 
     return trimLen;
 }
 
+// Downsampling (DownSampleTask, T.cpp:2164-2568): the reads are ranked by length, longest first, and
+// taken until the genome-size x depth / fraction / count target is met (get_reads_name,
+// T.cpp:2297-2344); the second pass then keeps the records whose NAME was selected, in file order.
+// Like the reference the ranking is keyed by read name (a later record with the same name replaces
+// the length of an earlier one, T.cpp:2135/2267).  Equal lengths at the cut-off are ordered by the
+// reference through std::sort over an unordered_map (unspecified); here ties keep file order.
+struct RecIndex {
+    std::vector<string> names;               // unique names in first-seen order
+    std::vector<int> lens;                   // current length per unique name
+    std::unordered_map<string, size_t> pos;  // name -> slot
+    void add(const string &name, int len) {
+        auto it = pos.find(name);
+        if (it == pos.end()) { pos.emplace(name, names.size()); names.push_back(name); lens.push_back(len); }
+        else lens[it->second] = len;
+    }
+};
+
+struct Selection {
+    std::vector<char> keep; // per unique-name slot
+    uint64_t downBases = 0, downNum = 0;
+};
+
+Selection select_reads(const RecIndex &idx, const Params &P) {
+    Selection S;
+    S.keep.assign(idx.names.size(), 0);
+    std::vector<size_t> order(idx.names.size());
+    for (size_t i = 0; i < order.size(); i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return idx.lens[a] > idx.lens[b]; });
+    uint64_t totalSize = 0;
+    for (int l : idx.lens) totalSize += (uint64_t)l;
+    auto take = [&](size_t i) { S.keep[i] = 1; S.downBases += (uint64_t)idx.lens[i]; S.downNum++; };
+    if (P.GenomeSize > 0 && P.DesiredDepth > 0) {
+        uint64_t added = 0, desired = P.GenomeSize * (uint64_t)P.DesiredDepth;
+        for (size_t i : order) { take(i); added += (uint64_t)idx.lens[i]; if (added >= desired) break; }
+    } else if (P.DesiredFrac > 0) {
+        uint64_t added = 0, desired = (uint64_t)(P.DesiredFrac * totalSize);
+        for (size_t i : order) { take(i); added += (uint64_t)idx.lens[i]; if (added >= desired) break; }
+    } else if (P.DesiredNum > 0) {
+        int n = 0;
+        for (size_t i : order) { take(i); if (++n >= P.DesiredNum) break; }
+    }
+    return S;
+}
+
 void die_tgsf(const char *what) {
     cerr << "Error: " << what << ": " << tgsf_last_error() << endl;
     exit(-1);
@@ -537,6 +589,12 @@ int main(int argc, char **argv) {
         }
     }
 
+    uint64_t cleanNum = 0, cleanBases = 0;
+    string tmpPath;
+    RecIndex recIdx;
+    std::vector<std::pair<uint64_t, uint32_t>> recSpan; // (offset, bytes) of every record in the tmp file
+    std::vector<size_t> recSlot;                         // unique-name slot of every record
+    if (P.Filter || P.OnlyQC) {
     // ---- contexts: one per GPU ---------------------------------------------------------------------
     tgsf_params tp;
     memset(&tp, 0, sizeof(tp));
@@ -559,14 +617,21 @@ int main(int argc, char **argv) {
 
     // ---- main pass -----------------------------------------------------------------------------------
     FILE *out = stdout;
-    if (!P.OnlyQC && !P.OutFile.empty()) {
+    uint64_t tmpBytes = 0;
+    if (P.Downsample) { // uncompressed tmp file like T.cpp:3129-3137
+        string prefix = P.InFile;
+        tmpPath = prefix + ".tmp." + std::to_string((long)getpid()) + (P.Outfq == 0 ? ".fa" : ".fq");
+        out = fopen(tmpPath.c_str(), "wb");
+        if (!out) { cerr << "Error: Failed to open file: " << tmpPath << endl; return 1; }
+    } else if (!P.OnlyQC && !P.OutFile.empty()) {
         out = fopen(P.OutFile.c_str(), "wb");
         if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
     }
+    const bool gz_now = P.OUTGZ && !P.Downsample; // T.cpp:2022
     const int slots = 2 * P.gpus;
     std::vector<Batch> ring((size_t)slots);
     std::deque<int> inflight; // ring indices in submission order; batch i runs on GPU (i % gpus)
-    uint64_t rawNum = 0, rawBases = 0, cleanNum = 0, cleanBases = 0, submitted = 0;
+    uint64_t rawNum = 0, rawBases = 0, submitted = 0;
     std::vector<tgsf_read_result> rr;
     std::vector<tgsf_piece> pc;
 
@@ -602,10 +667,16 @@ int main(int argc, char **argv) {
             } else {
                 rec += '>'; rec += name; rec += '\n'; rec.append(s, p.len); rec += '\n';
             }
-            if (P.OUTGZ) {
+            if (gz_now) {
                 if (gz_member(rec, P.compLevel, gz)) fwrite(gz.data(), 1, gz.size(), out);
             } else {
                 fwrite(rec.data(), 1, rec.size(), out);
+            }
+            if (P.Downsample) {
+                recIdx.add(name, p.len);
+                recSlot.push_back(recIdx.pos[name]);
+                recSpan.emplace_back(tmpBytes, (uint32_t)rec.size());
+                tmpBytes += rec.size();
             }
             cleanNum++;
             cleanBases += (uint64_t)p.len;
@@ -666,7 +737,7 @@ int main(int argc, char **argv) {
         if (P.MinRepeat > 0)
             cerr << "INFO: " << D[15] << " reads were discarded with " << D[16] << " bases due to short repeat length." << endl;
         cerr << "INFO: " << cleanNum << " reads with a total of " << cleanBases << " bases after filtering." << endl;
-        if (!P.OutFile.empty()) cerr << "INFO: Filtered reads were written to: " << P.OutFile << "." << endl;
+        if (!P.Downsample && !P.OutFile.empty()) cerr << "INFO: Filtered reads were written to: " << P.OutFile << "." << endl;
     }
     if (const char *dump = getenv("TGSF_DUMP_COUNTERS")) { // raw counter block for report tooling / tests
         FILE *f = fopen(dump, "wb");
@@ -678,5 +749,63 @@ int main(int argc, char **argv) {
     }
     for (Batch &b : ring) b.release();
     for (tgsf_ctx *c : ctx) tgsf_destroy(c);
+    }
+
+    // ---- downsampling: DownSampleTask (T.cpp:2164-2568) -------------------------------------------
+    if (P.Downsample) {
+        FILE *fout = stdout;
+        if (!P.OutFile.empty()) {
+            fout = fopen(P.OutFile.c_str(), "wb");
+            if (!fout) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
+        }
+        string gz;
+        auto emit = [&](const char *data, size_t n) {
+            if (P.OUTGZ) {
+                if (gz_member(string(data, n), P.compLevel, gz)) fwrite(gz.data(), 1, gz.size(), fout);
+            } else {
+                fwrite(data, 1, n, fout);
+            }
+        };
+        Selection S;
+        if (P.Filter) {
+            S = select_reads(recIdx, P);
+            FILE *tin = fopen(tmpPath.c_str(), "rb");
+            if (!tin) { cerr << "Error: Failed to open file: " << tmpPath << endl; return 1; }
+            std::vector<char> buf;
+            for (size_t i = 0; i < recSpan.size(); i++) {
+                if (!S.keep[recSlot[i]]) continue;
+                buf.resize(recSpan[i].second);
+                if (fseeko(tin, (off_t)recSpan[i].first, SEEK_SET) != 0 || fread(buf.data(), 1, buf.size(), tin) != buf.size()) {
+                    cerr << "Error: short read from " << tmpPath << endl;
+                    return 1;
+                }
+                emit(buf.data(), buf.size());
+            }
+            fclose(tin);
+        } else { // -F: straight from the input file (get_fastx_SeqLen + read_fastx, T.cpp:2256-2269, 2346-2368)
+            uint64_t downInNum = 0, downInBases = 0;
+            {
+                FastxReader rd(P.InFile);
+                string name, seq, qual;
+                while (rd.read(name, seq, qual)) { recIdx.add(name, (int)seq.size()); downInNum++; downInBases += seq.size(); }
+            }
+            S = select_reads(recIdx, P);
+            FastxReader rd(P.InFile);
+            string name, seq, qual, rec;
+            while (rd.read(name, seq, qual)) {
+                auto it = recIdx.pos.find(name);
+                if (it == recIdx.pos.end() || !S.keep[it->second]) continue;
+                rec.clear();
+                if (P.Outfq == 1) { rec += '@'; rec += name; rec += '\n'; rec += seq; rec += "\n+\n"; rec += qual; rec += '\n'; }
+                else { rec += '>'; rec += name; rec += '\n'; rec += seq; rec += '\n'; }
+                emit(rec.data(), rec.size());
+            }
+            cerr << "INFO: " << downInNum << " reads with a total of " << downInBases << " bases were input." << endl;
+        }
+        if (fout != stdout) fclose(fout);
+        cerr << "INFO: " << S.downNum << " reads with a total of " << S.downBases << " bases after downsampling." << endl;
+        if (!P.OutFile.empty()) cerr << "INFO: Downsampled reads were written to: " << P.OutFile << "." << endl;
+        if (!tmpPath.empty()) remove(tmpPath.c_str());
+    }
     return 0;
 }

