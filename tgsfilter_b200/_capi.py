@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtgsf_cuda.so")
+LIB_PATH = os.environ.get("TGSF_LIB_PATH") or os.path.join(_HERE, "libtgsf_cuda.so")  # override: A/B builds
 
 TGSF_OK = 0
 TGSF_ERR_INVALID = 1

@@ -1021,6 +1021,7 @@ int tgsf_counters_device(tgsf_ctx *c, void **d_ptr, uint32_t *n_u64) {
 
 uint64_t tgsf_launch_count(const tgsf_ctx *c) { return c ? c->launches : 0; }
 
+
 int tgsf_allreduce(tgsf_ctx **ctxs, int n) {
     if (!ctxs || n <= 0) { set_err("allreduce: no contexts"); return TGSF_ERR_INVALID; }
     for (int i = 0; i < n; ++i) {
