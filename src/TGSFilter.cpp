@@ -31,6 +31,7 @@
 
 #include "../include/tgsf.h"
 #include "../include/tgsf_layout.h"
+#include "report.hpp"
 
 using std::cerr;
 using std::endl;
@@ -538,8 +539,15 @@ int main(int argc, char **argv) {
                          search ? lib_seq.data() : nullptr, lib_len.data(), TGSF_LIB_ADAPTERS, P.MidSim, bn5.data(),
                          bn3.data(), m5.data(), m3.data()) != TGSF_OK)
             die_tgsf("tgsf_prepass");
-        if (P.HeadTrim < 0) P.HeadTrim = base_content_trim(bn5, checkLen, seqNum, P.EndBias);
-        if (P.TailTrim < 0) P.TailTrim = base_content_trim(bn3, checkLen, seqNum, P.EndBias);
+        // Both CheckBaseContent threads clamp trim5p to BCLen BEFORE storing their own result
+        // (T.cpp:1136-1144), so the 5' trim is clamped only if the 3' thread finishes after the 5' one
+        // has stored it: a race in the reference.  Resolved here in thread-creation order (5' first).
+        const bool auto5 = P.HeadTrim < 0, auto3 = P.TailTrim < 0;
+        if (auto5) P.HeadTrim = base_content_trim(bn5, checkLen, seqNum, P.EndBias);
+        if (auto3) {
+            if (auto5 && P.HeadTrim > P.BCLen) P.HeadTrim = P.BCLen;
+            P.TailTrim = base_content_trim(bn3, checkLen, seqNum, P.EndBias);
+        }
         cerr << "INFO: trim 5' end length: " << P.HeadTrim << endl;
         cerr << "INFO: trim 3' end length: " << P.TailTrim << endl;
         cerr << "INFO: min output reads length: " << P.MinLen << endl;
@@ -589,7 +597,9 @@ int main(int argc, char **argv) {
         }
     }
 
-    uint64_t cleanNum = 0, cleanBases = 0;
+    uint64_t cleanNum = 0, cleanBases = 0, rawNum = 0, rawBases = 0;
+    std::vector<int> rawLens, cleanLens;       // T.cpp:1794
+    report::Side rawSide, cleanSide;
     string tmpPath;
     RecIndex recIdx;
     std::vector<std::pair<uint64_t, uint32_t>> recSpan; // (offset, bytes) of every record in the tmp file
@@ -631,7 +641,7 @@ int main(int argc, char **argv) {
     const int slots = 2 * P.gpus;
     std::vector<Batch> ring((size_t)slots);
     std::deque<int> inflight; // ring indices in submission order; batch i runs on GPU (i % gpus)
-    uint64_t rawNum = 0, rawBases = 0, submitted = 0;
+    uint64_t submitted = 0;
     std::vector<tgsf_read_result> rr;
     std::vector<tgsf_piece> pc;
 
@@ -680,6 +690,7 @@ int main(int argc, char **argv) {
             }
             cleanNum++;
             cleanBases += (uint64_t)p.len;
+            cleanLens.push_back(p.len);
         }
         b.clear();
     };
@@ -700,6 +711,7 @@ int main(int argc, char **argv) {
         while (rd.read(name, seq, qual)) {
             rawNum++;
             rawBases += seq.size();
+            rawLens.push_back((int)seq.size());
             Batch &b = ring[(size_t)cur];
             if (!b.add(name, seq, qual, has_qual)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
             if (b.used >= P.batch_bases) {
@@ -739,6 +751,10 @@ int main(int argc, char **argv) {
         cerr << "INFO: " << cleanNum << " reads with a total of " << cleanBases << " bases after filtering." << endl;
         if (!P.Downsample && !P.OutFile.empty()) cerr << "INFO: Filtered reads were written to: " << P.OutFile << "." << endl;
     }
+    // report columns (T.cpp:3146-3206)
+    report::build_side(rawLens, rawBases, P.BCLen, has_qual, C.data(), L, false, 3, rawSide);
+    if (!P.OnlyQC && !P.Downsample && cleanNum)
+        report::build_side(cleanLens, cleanBases, P.BCLen, has_qual, C.data(), L, true, 3, cleanSide);
     if (const char *dump = getenv("TGSF_DUMP_COUNTERS")) { // raw counter block for report tooling / tests
         FILE *f = fopen(dump, "wb");
         if (f) {
@@ -767,30 +783,37 @@ int main(int argc, char **argv) {
             }
         };
         Selection S;
-        if (P.Filter) {
-            S = select_reads(recIdx, P);
-            FILE *tin = fopen(tmpPath.c_str(), "rb");
-            if (!tin) { cerr << "Error: Failed to open file: " << tmpPath << endl; return 1; }
-            std::vector<char> buf;
-            for (size_t i = 0; i < recSpan.size(); i++) {
-                if (!S.keep[recSlot[i]]) continue;
-                buf.resize(recSpan[i].second);
-                if (fseeko(tin, (off_t)recSpan[i].first, SEEK_SET) != 0 || fread(buf.data(), 1, buf.size(), tin) != buf.size()) {
-                    cerr << "Error: short read from " << tmpPath << endl;
-                    return 1;
-                }
-                emit(buf.data(), buf.size());
-            }
-            fclose(tin);
-        } else { // -F: straight from the input file (get_fastx_SeqLen + read_fastx, T.cpp:2256-2269, 2346-2368)
-            uint64_t downInNum = 0, downInBases = 0;
-            {
-                FastxReader rd(P.InFile);
-                string name, seq, qual;
-                while (rd.read(name, seq, qual)) { recIdx.add(name, (int)seq.size()); downInNum++; downInBases += seq.size(); }
-            }
-            S = select_reads(recIdx, P);
+        uint64_t downInNum = 0, downInBases = 0;
+        const string downInput = P.Filter ? tmpPath : P.InFile;
+        if (!P.Filter) { // get_fastx_SeqLen, T.cpp:2256-2269
             FastxReader rd(P.InFile);
+            string name, seq, qual;
+            while (rd.read(name, seq, qual)) { recIdx.add(name, (int)seq.size()); downInNum++; downInBases += seq.size(); }
+        }
+        S = select_reads(recIdx, P);
+        // second pass (T.cpp:2346-2568): keep the selected names in file order and recompute the QC
+        // tables of the kept reads on the GPU (a QC-only context: its "raw" tables are the report's
+        // "after" column)
+        tgsf_params qp;
+        memset(&qp, 0, sizeof(qp));
+        qp.bc_len = P.BCLen; qp.qtype = qType; qp.flags = TGSF_FLAG_ONLY_QC; qp.max_q = 255; qp.min_q = -1; qp.n_slots = 1;
+        tgsf_ctx *qctx = nullptr;
+        if (tgsf_create(0, &qp, &qctx) != TGSF_OK) die_tgsf("tgsf_create (downsample QC)");
+        Batch qb;
+        const bool dqual = file_type(downInput) == 1;
+        auto flush = [&]() {
+            if (!qb.n()) return;
+            if (!qb.pack()) die_tgsf("tgsf_pack_bases");
+            if (tgsf_submit_packed(qctx, qb.packed, dqual ? qb.quals : nullptr, qb.offsets.data(), qb.n(), qb.exc_pos.data(),
+                                   qb.exc_byte.data(), qb.n_exc) != TGSF_OK)
+                die_tgsf("tgsf_submit_packed");
+            if (tgsf_collect(qctx, nullptr, 0, nullptr, 0, nullptr) != TGSF_OK) die_tgsf("tgsf_collect");
+            qb.clear();
+        };
+        std::vector<int> downLens;
+        uint64_t downBases = 0;
+        {
+            FastxReader rd(downInput);
             string name, seq, qual, rec;
             while (rd.read(name, seq, qual)) {
                 auto it = recIdx.pos.find(name);
@@ -799,13 +822,47 @@ int main(int argc, char **argv) {
                 if (P.Outfq == 1) { rec += '@'; rec += name; rec += '\n'; rec += seq; rec += "\n+\n"; rec += qual; rec += '\n'; }
                 else { rec += '>'; rec += name; rec += '\n'; rec += seq; rec += '\n'; }
                 emit(rec.data(), rec.size());
+                if (!qb.add(name, seq, qual, dqual)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
+                if (qb.used >= P.batch_bases) flush();
             }
-            cerr << "INFO: " << downInNum << " reads with a total of " << downInBases << " bases were input." << endl;
+            flush();
         }
+        // the reference's table / length plots use the selection list (T.cpp:3244-3256)
+        for (size_t i = 0; i < recIdx.names.size(); i++)
+            if (S.keep[i]) { downLens.push_back(recIdx.lens[i]); downBases += (uint64_t)recIdx.lens[i]; }
+        {
+            tgsf_counter_layout QL;
+            tgsf_counter_layout_get(qctx, &QL);
+            std::vector<uint64_t> QC(QL.n_u64);
+            if (tgsf_counters(qctx, QC.data(), QL.n_u64) != TGSF_OK) die_tgsf("tgsf_counters");
+            report::build_side(downLens, downBases, P.BCLen, dqual, QC.data(), QL, false, 2, cleanSide);
+        }
+        qb.release();
+        tgsf_destroy(qctx);
+        if (!P.Filter) cerr << "INFO: " << downInNum << " reads with a total of " << downInBases << " bases were input." << endl;
         if (fout != stdout) fclose(fout);
         cerr << "INFO: " << S.downNum << " reads with a total of " << S.downBases << " bases after downsampling." << endl;
         if (!P.OutFile.empty()) cerr << "INFO: Downsampled reads were written to: " << P.OutFile << "." << endl;
         if (!tmpPath.empty()) remove(tmpPath.c_str());
+    }
+
+    // ---- QC report (T.cpp:3285-3328) -----------------------------------------------------------------
+    {
+        auto prefix_of = [](const string &path) { // GetFilePreifx, T.cpp:824-837
+            string ext = file_ext(path), prefix = path;
+            if (ext == "gz") { prefix = path.substr(0, path.rfind('.')); ext = file_ext(prefix); }
+            if (ext == "fq" || ext == "fastq" || ext == "fa" || ext == "fasta" || ext == "bam" || ext == "sam" || ext == "BAM" || ext == "SAM")
+                prefix = prefix.substr(0, prefix.rfind('.'));
+            return prefix;
+        };
+        string html = prefix_of(P.InFile) + ".html";
+        if (!P.OutFile.empty() && !P.OnlyQC) html = prefix_of(P.OutFile) + ".html";
+        string qcType = P.Infq == 0 ? "0" : "1";
+        if (P.OnlyQC) qcType += "0";
+        else if (!P.Filter && P.Downsample) qcType += "1";
+        else qcType += "2";
+        report::write_html(html, qcType, rawSide, cleanSide);
+        cerr << "INFO: Quality control report was written to: " << html << "." << endl;
     }
     return 0;
 }

@@ -500,3 +500,78 @@ def test_host_cli_downsampling_vs_reference_cli(args):
     assert (h_rc, r_rc) == (0, 0), h_err
     assert h_out == r_out
     assert _info(h_err) == _info(r_err)
+
+
+def _run_host_cli_html(args, fastq: bytes, in_name="in.fq", out_name="out.fq"):
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "src", "tgsfilter")
+    with tempfile.TemporaryDirectory() as td:
+        fi = os.path.join(td, in_name)
+        with open(fi, "wb") as f:
+            f.write(fastq)
+        cmd = [exe, "-i", fi] + list(args)
+        if out_name:
+            cmd += ["-o", os.path.join(td, out_name)]
+        pr = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600, cwd=td)
+        html = ""
+        for fn in os.listdir(td):
+            if fn.endswith(".html"):
+                with open(os.path.join(td, fn), "r", errors="replace") as f:
+                    html = f.read()
+        return pr.returncode, pr.stderr.decode("utf-8", "replace"), html
+
+
+def _report_parts(html: str):
+    import re
+    m = re.search(r"var data = \{\n(.*?)\}\n</script>", html, re.S)
+    assert m, "no `var data` block in the report"
+    cells = re.findall(r"<td>(.*?)</td>", html)
+    return m.group(1), cells
+
+
+@pytest.mark.parametrize("cfg,n,args,in_name,out_name", [
+    (1, 300, ["-x", "hifi"], "in.fq", "out.fq"),
+    (2, 300, ["-x", "ont"], "in.fq", "out.fq"),
+    (3, 50, ["-x", "ont", "-D"], "in.fq", "out.fq"),
+    (4, 500, ["-x", "clr", "-q", "7", "-Q", "15", "-e", "120"], "in.fq", "out.fq"),
+    (2, 200, ["--qc"], "in.fq", None),
+    (1, 200, ["-x", "hifi", "-f"], "in.fa", "out.fa"),
+])
+def test_host_cli_qc_report_data_vs_reference(cfg, n, args, in_name, out_name):
+    """The `var data` block and the summary table of the HTML report."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not present")
+    batch = synth.make_config(cfg, n, max_len=90000)
+    data = batch.to_fasta() if in_name.endswith(".fa") else batch.to_fastq()
+    if in_name.endswith(".fa"):
+        args = [a for a in args if a != "-f"]
+    r_rc, _, r_err, r_html = ref_lib.run_cli(args + ["-t", "1"], data, in_name=in_name, out_name=out_name)
+    h_rc, h_err, h_html = _run_host_cli_html(args, data, in_name=in_name, out_name=out_name)
+    assert (h_rc, r_rc) == (0, 0), h_err
+    r_data, r_cells = _report_parts(r_html)
+    h_data, h_cells = _report_parts(h_html)
+    assert h_cells == r_cells
+    assert h_data == r_data
+
+
+@pytest.mark.parametrize("args", [
+    ["-x", "hifi", "-r", "41", "-5", "0", "-3", "0"],
+    ["-F", "-r", "25"],
+])
+def test_host_cli_downsample_report_vs_reference(args):
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not present")
+    batch = _distinct_length_batch(5, 200)
+    fq = batch.to_fastq()
+    r_rc, _, r_err, r_html = ref_lib.run_cli(args + ["-t", "1"], fq)
+    h_rc, h_err, h_html = _run_host_cli_html(args, fq)
+    assert (h_rc, r_rc) == (0, 0), h_err
+    r_data, r_cells = _report_parts(r_html)
+    h_data, h_cells = _report_parts(h_html)
+    assert h_cells == r_cells
+    assert h_data == r_data

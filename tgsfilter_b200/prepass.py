@@ -136,6 +136,10 @@ def resolve(c5, c3, m5, m3, *, n: int, end_bias: float, mid_sim: float, bc_len: 
     log = []
     t5 = base_content_trim(c5, n, end_bias) if head_trim < 0 else head_trim
     t3 = base_content_trim(c3, n, end_bias) if tail_trim < 0 else tail_trim
+    # the reference clamps trim5p to BCLen before each thread stores its result (T.cpp:1136-1144): a race;
+    # resolved in thread-creation order (5' thread first, so the 3' thread's clamp sees the 5' result)
+    if head_trim < 0 and tail_trim < 0 and t5 > bc_len:
+        t5 = bc_len
     log.append(f"INFO: trim 5' end length: {t5}")
     log.append(f"INFO: trim 3' end length: {t3}")
     a5 = a3 = b""
