@@ -1,0 +1,27 @@
+import os, sys, time, subprocess, tempfile
+sys.path.insert(0, os.getcwd())
+from tgsfilter_b200 import synth
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+ext = sys.argv[2] if len(sys.argv) > 2 else ".fq"   # ".fq.gz": per-record gzip members like the reference
+batch = synth.make_config(2, n, with_names=False)
+d = "/dev/shm/f2f"; os.makedirs(d, exist_ok=True)
+fq = os.path.join(d, "in.fq")
+with open(fq, "wb") as f: f.write(batch.to_fastq())
+n_bases = batch.n_bases
+del batch
+print("bases", n_bases, "file MB", os.path.getsize(fq) / 1e6)
+for name, exe, extra in (("host_b200", "src/tgsfilter", []), ("reference", "oracle/_ref/tgsfilter", ["-t", str(min(32, (os.cpu_count() or 2) - 1))])):
+    out = os.path.join(d, name + ext)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        pr = subprocess.run([exe, "-i", fq, "-x", "ont", "-o", out] + extra, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+        dt = time.perf_counter() - t0
+        print(name, "rc", pr.returncode, "%.2f s" % dt, "%.3f Gbases/s" % (n_bases / dt / 1e9))
+def slurp(path):
+    import gzip
+    if path.endswith(".gz"):  # streaming reader: gzip.decompress() is quadratic in the number of members
+        with gzip.open(path, "rb") as f:
+            return f.read()
+    return open(path, "rb").read()
+a = slurp(os.path.join(d, "host_b200" + ext)); b = slurp(os.path.join(d, "reference" + ext))
+print("same multiset of records:", sorted(a.split(b"@read")) == sorted(b.split(b"@read")), len(a), len(b))

@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <cctype>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -27,10 +28,13 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <sys/stat.h>
+#include <sys/uio.h>
 #include <unistd.h>
 
 #include "../include/tgsf.h"
 #include "../include/tgsf_layout.h"
+#include "pipeline.hpp"
 #include "report.hpp"
 
 using std::cerr;
@@ -61,7 +65,7 @@ struct Params {
     bool OUTGZ = false;
     int compLevel = 6;
     int gpus = 1;                 // --gpus (extension; TGSF_GPUS env)
-    uint64_t batch_bases = 256ull << 20;
+    uint64_t batch_bases = 64ull << 20; // bases per batch (TGSF_BATCH_MB)
 };
 
 int usage() {
@@ -444,6 +448,13 @@ Selection select_reads(const RecIndex &idx, const Params &P) {
     return S;
 }
 
+struct Timer { // TGSF_TIMING=1: phase timings on stderr
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap() { auto t1 = std::chrono::steady_clock::now(); double d = std::chrono::duration<double>(t1 - t0).count(); t0 = t1; return d; }
+};
+bool g_timing = false;
+void tlog(const char *what, double s) { if (g_timing) cerr << "[timing] " << what << ": " << s << " s" << endl; }
+
 void die_tgsf(const char *what) {
     cerr << "Error: " << what << ": " << tgsf_last_error() << endl;
     exit(-1);
@@ -453,6 +464,9 @@ void die_tgsf(const char *what) {
 
 int main(int argc, char **argv) {
     Params P;
+    g_timing = getenv("TGSF_TIMING") != nullptr;
+    Timer T_all, T_ph;
+    const bool clean_exit = getenv("TGSF_CLEAN_EXIT") != nullptr; // destroy contexts / free buffers before returning
     if (const char *e = getenv("TGSF_GPUS")) P.gpus = std::max(1, atoi(e));
     if (parse_cmd(argc, argv, &P) == 1) return 1;
     for (int i = 0; i < 256; i++) g_comp[i] = 'N';
@@ -483,7 +497,48 @@ int main(int argc, char **argv) {
     int maxSeq = std::max(P.ADNum, P.BCNum);
     std::vector<uint8_t> e5, e3;
     int seqNum = 0, minQ = 255, maxQ = 0;
-    {
+    // One pass over the input: the reader thread parses batches; the pre-pass samples read ends from
+    // them as they arrive and keeps them (pageable) for the main pass, which then carries on with the
+    // rest of the stream — the reference reads the head of the file twice (T.cpp:949-982, 1845-1870).
+    const uint64_t batch_bases = getenv("TGSF_BATCH_MB") ? (uint64_t)atoll(getenv("TGSF_BATCH_MB")) << 20 : P.batch_bases;
+    ingest::Queue<std::unique_ptr<ingest::RawBatch>> parsed(4);
+    ingest::BatchPool batch_pool;
+    std::deque<std::unique_ptr<ingest::RawBatch>> pending;
+    bool input_done = false;
+    std::thread reader;
+    std::unique_ptr<ingest::ParallelReader> preader; // plain files: parallel chunk parser
+    auto next_parsed = [&]() { return preader ? preader->pop() : parsed.pop(); };
+    const bool stream_input = P.Filter || P.OnlyQC;
+    if (stream_input) {
+        { gzFile probe = gzopen(P.InFile.c_str(), "rb"); if (!probe) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; } gzclose(probe); }
+        if (!ingest::ParallelReader::is_gzip(P.InFile) && !getenv("TGSF_SERIAL_READER")) {
+            const int hw = (int)std::thread::hardware_concurrency();
+            const int nthr = getenv("TGSF_PARSE_THREADS") ? atoi(getenv("TGSF_PARSE_THREADS")) : std::max(1, std::min(8, hw - 2));
+            preader.reset(new ingest::ParallelReader(P.InFile, has_qual, 2 * batch_bases, nthr, &batch_pool));
+            if (!preader->ok()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
+        } else {
+            reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool);
+        }
+        { Timer tw; void *warm = nullptr; if (tgsf_host_alloc(&warm, 1 << 20) == TGSF_OK) tgsf_host_free(warm); tlog("  CUDA context warm-up", tw.lap()); } // CUDA context up while the reader parses
+        while (!input_done && seqNum < maxSeq) {
+            std::unique_ptr<ingest::RawBatch> rb = next_parsed();
+            if (!rb) { input_done = true; break; }
+            for (uint32_t i = 0; i < rb->n() && seqNum < maxSeq; i++) {
+                const uint64_t s0 = rb->offsets[i];
+                const int L = (int)(rb->offsets[i + 1] - s0);
+                if (L < minLen) continue;
+                seqNum++;
+                e5.insert(e5.end(), rb->bases.begin() + s0, rb->bases.begin() + s0 + checkLen);
+                for (int j = 0; j < checkLen; j++) e3.push_back((uint8_t)g_comp[rb->bases[s0 + L - 1 - j]]);
+                for (int j = 0; j < checkLen && has_qual; j++) {
+                    char q = (char)rb->quals[s0 + j];
+                    if (minQ > q) minQ = q;
+                    if (maxQ < q) maxQ = q;
+                }
+            }
+            pending.push_back(std::move(rb));
+        }
+    } else { // -F: only the sample is needed here; DownSampleTask reads the file itself
         FastxReader rd(P.InFile);
         if (!rd.ok()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
         string name, seq, qual;
@@ -492,9 +547,6 @@ int main(int argc, char **argv) {
             if (L < minLen) continue;
             if (seqNum >= maxSeq) break;
             seqNum++;
-            e5.insert(e5.end(), seq.begin(), seq.begin() + checkLen);
-            string t = rev_comp(seq.substr(L - checkLen));
-            e3.insert(e3.end(), t.begin(), t.end());
             for (int i = 0; i < checkLen && has_qual; i++) {
                 char q = qual[i];
                 if (minQ > q) minQ = q;
@@ -502,6 +554,7 @@ int main(int argc, char **argv) {
             }
         }
     }
+    tlog("prepass sampling (incl. CUDA context)", T_ph.lap());
     int qType = 0;
     if (has_qual) {
         if (minQ >= 33 && minQ <= 78 && maxQ >= 33 && maxQ <= 127) qType = 33;
@@ -602,9 +655,8 @@ int main(int argc, char **argv) {
     report::Side rawSide, cleanSide;
     string tmpPath;
     RecIndex recIdx;
-    std::vector<std::pair<uint64_t, uint32_t>> recSpan; // (offset, bytes) of every record in the tmp file
-    std::vector<size_t> recSlot;                         // unique-name slot of every record
     if (P.Filter || P.OnlyQC) {
+    tlog("gpu prepass + resolve", T_ph.lap());
     // ---- contexts: one per GPU ---------------------------------------------------------------------
     tgsf_params tp;
     memset(&tp, 0, sizeof(tp));
@@ -625,9 +677,9 @@ int main(int argc, char **argv) {
     for (int g = 0; g < P.gpus; g++)
         if (tgsf_create(g, &tp, &ctx[(size_t)g]) != TGSF_OK) die_tgsf("tgsf_create");
 
+    tlog("tgsf_create", T_ph.lap());
     // ---- main pass -----------------------------------------------------------------------------------
     FILE *out = stdout;
-    uint64_t tmpBytes = 0;
     if (P.Downsample) { // uncompressed tmp file like T.cpp:3129-3137
         string prefix = P.InFile;
         tmpPath = prefix + ".tmp." + std::to_string((long)getpid()) + (P.Outfq == 0 ? ".fa" : ".fq");
@@ -638,91 +690,272 @@ int main(int argc, char **argv) {
         if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
     }
     const bool gz_now = P.OUTGZ && !P.Downsample; // T.cpp:2022
+    // pinned staging ring: what crosses PCIe (2-bit packed bases, Phred bytes); 2 slots per GPU
+    struct PinSlot {
+        uint8_t *packed = nullptr, *quals = nullptr;
+        size_t cap = 0;
+        std::vector<uint64_t> exc_pos;
+        std::vector<uint8_t> exc_byte;
+        std::unique_ptr<ingest::RawBatch> rb;
+        bool reserve(size_t bases) {
+            if (bases <= cap) return true;
+            tgsf_host_free(packed);
+            tgsf_host_free(quals);
+            cap = bases + bases / 4 + (1 << 20);
+            return tgsf_host_alloc((void **)&packed, cap / 4 + 64) == TGSF_OK && tgsf_host_alloc((void **)&quals, cap) == TGSF_OK;
+        }
+    };
     const int slots = 2 * P.gpus;
-    std::vector<Batch> ring((size_t)slots);
-    std::deque<int> inflight; // ring indices in submission order; batch i runs on GPU (i % gpus)
-    uint64_t submitted = 0;
-    std::vector<tgsf_read_result> rr;
-    std::vector<tgsf_piece> pc;
+    std::vector<PinSlot> ring((size_t)slots);
+    std::deque<int> inflight; // ring indices in submission order; slot i runs on GPU (i % gpus)
 
+    // writer thread (T.cpp:2011-2053): numbers the emitted pieces of a retired batch, then
+    //  * plain output: gathers name/bases/qualities straight out of the batch with (p)writev, no
+    //    formatting copy; a regular file is written by several threads at precomputed offsets;
+    //  * gzip output: one member per record like DeflateCompress (T.cpp:786-812), the records of a
+    //    batch spread over -t compressor threads, written in order;
+    //  * downsampling: the serial path (uncompressed tmp file + record index).
+    struct WriteJob { std::unique_ptr<ingest::RawBatch> rb; std::vector<tgsf_piece> pieces; };
+    struct Emit { uint32_t read, start, len; int pass; };
+    ingest::Queue<std::unique_ptr<WriteJob>> to_write(4);
+    const int out_threads = std::max(1, std::min(P.n_thread, (int)std::thread::hardware_concurrency()));
+    fflush(out);
+    const int out_fd = fileno(out);
+    struct stat out_st;
+    // positioned parallel writes only into a file this process created (stdout may be in append mode)
+    const bool out_regular = out != stdout && fstat(out_fd, &out_st) == 0 && S_ISREG(out_st.st_mode) && !getenv("TGSF_SERIAL_WRITER");
+    uint64_t out_off = 0; // regular file: bytes written so far
+    std::thread writer([&]() {
+        string obuf, rec, gz;
+        std::vector<Emit> emits;
+        std::vector<string> renamed; // names with a :N suffix, alive until the batch is written
+        std::vector<string> bufs;
+        while (true) {
+            std::unique_ptr<WriteJob> job = to_write.pop();
+            if (!job) break;
+            const ingest::RawBatch &b = *job->rb;
+            emits.clear();
+            renamed.clear();
+            uint32_t last = UINT32_MAX;
+            int pass = 1;
+            for (const tgsf_piece &p : job->pieces) { // T.cpp:1976-2059
+                if ((uint32_t)p.read != last) { last = (uint32_t)p.read; pass = 1; }
+                if (p.status != TGSF_PIECE_EMIT) continue;
+                emits.push_back(Emit{last, (uint32_t)p.start, (uint32_t)p.len, pass});
+                pass++;
+                cleanNum++;
+                cleanBases += (uint64_t)p.len;
+                cleanLens.push_back(p.len);
+            }
+            // names: pass 1 keeps the raw name, later pieces get ":N" before the first blank
+            std::vector<const string *> nm(emits.size());
+            {
+                size_t nren = 0;
+                for (const Emit &e : emits) nren += e.pass >= 2;
+                renamed.reserve(nren);
+                for (size_t i = 0; i < emits.size(); ++i) {
+                    if (emits[i].pass >= 2) { renamed.push_back(new_seq_name(b.names[emits[i].read], emits[i].pass)); nm[i] = &renamed.back(); }
+                    else nm[i] = &b.names[emits[i].read];
+                }
+            }
+            auto format_rec = [&](size_t i, string &dst) {
+                const Emit &e = emits[i];
+                const char *sq = (const char *)b.bases.data() + b.offsets[e.read] + e.start;
+                if (P.Outfq == 1) {
+                    const char *q = (const char *)b.quals.data() + b.offsets[e.read] + e.start;
+                    dst += '@'; dst += *nm[i]; dst += '\n'; dst.append(sq, e.len); dst += "\n+\n"; dst.append(q, e.len); dst += '\n';
+                } else {
+                    dst += '>'; dst += *nm[i]; dst += '\n'; dst.append(sq, e.len); dst += '\n';
+                }
+            };
+            if (P.Downsample) {
+                for (size_t i = 0; i < emits.size(); ++i) {
+                    format_rec(i, obuf);
+                    recIdx.add(*nm[i], (int)emits[i].len);
+                    if (obuf.size() >= (8u << 20)) { fwrite(obuf.data(), 1, obuf.size(), out); obuf.clear(); }
+                }
+                if (!obuf.empty()) { fwrite(obuf.data(), 1, obuf.size(), out); obuf.clear(); }
+            } else if (!emits.empty()) {
+                // split the records into contiguous ranges of about equal payload
+                const int K = gz_now ? out_threads : (out_regular ? std::min(out_threads, 4) : 1);
+                std::vector<size_t> cut((size_t)K + 1, emits.size());
+                std::vector<uint64_t> bytes_before((size_t)K + 1, 0);
+                {
+                    uint64_t total = 0;
+                    for (const Emit &e : emits) total += e.len;
+                    uint64_t acc = 0, raw = 0;
+                    int k = 0;
+                    cut[0] = 0;
+                    for (size_t i = 0; i < emits.size(); ++i) {
+                        while (k + 1 < K && acc >= total * (uint64_t)(k + 1) / (uint64_t)K) { cut[(size_t)++k] = i; bytes_before[(size_t)k] = raw; }
+                        acc += emits[i].len;
+                        const uint64_t nl = nm[i]->size();
+                        raw += P.Outfq == 1 ? 1 + nl + 1 + emits[i].len + 3 + emits[i].len + 1 : 1 + nl + 1 + emits[i].len + 1;
+                    }
+                    while (k + 1 < K) { cut[(size_t)++k] = emits.size(); bytes_before[(size_t)k] = raw; }
+                    bytes_before[(size_t)K] = raw;
+                }
+                if (gz_now) {
+                    bufs.resize((size_t)K);
+                    auto compress_range = [&](int k) {
+                        string &dst = bufs[(size_t)k];
+                        dst.clear();
+                        string r;
+                        z_stream zs;
+                        memset(&zs, 0, sizeof(zs));
+                        if (deflateInit2(&zs, P.compLevel, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return;
+                        for (size_t i = cut[(size_t)k]; i < cut[(size_t)k + 1]; ++i) {
+                            r.clear();
+                            format_rec(i, r);
+                            deflateReset(&zs);
+                            const size_t at = dst.size(), bound = deflateBound(&zs, r.size()) + 32;
+                            dst.resize(at + bound);
+                            zs.next_in = (Bytef *)r.data();
+                            zs.avail_in = (uInt)r.size();
+                            zs.next_out = (Bytef *)&dst[at];
+                            zs.avail_out = (uInt)bound;
+                            deflate(&zs, Z_FINISH);
+                            dst.resize(at + zs.total_out);
+                        }
+                        deflateEnd(&zs);
+                    };
+                    std::vector<std::thread> th;
+                    for (int k = 1; k < K; ++k) th.emplace_back(compress_range, k);
+                    compress_range(0);
+                    for (auto &t : th) t.join();
+                    for (int k = 0; k < K; ++k) {
+                        const string &d = bufs[(size_t)k];
+                        size_t done = 0;
+                        while (done < d.size()) {
+                            const ssize_t w = write(out_fd, d.data() + done, d.size() - done);
+                            if (w <= 0) { cerr << "Error: write failed" << endl; exit(-1); }
+                            done += (size_t)w;
+                        }
+                    }
+                } else {
+                    static const char kAt = '@', kGt = '>', kNl = '\n';
+                    static const char kPlus[] = "\n+\n";
+                    auto write_range = [&](int k) {
+                        std::vector<struct iovec> iov;
+                        iov.reserve(1024);
+                        uint64_t off = out_off + bytes_before[(size_t)k];
+                        auto flush = [&]() {
+                            size_t first = 0;
+                            while (first < iov.size()) {
+                                const int cnt = (int)std::min<size_t>(iov.size() - first, 1024);
+                                ssize_t w = out_regular ? pwritev(out_fd, iov.data() + first, cnt, (off_t)off) : writev(out_fd, iov.data() + first, cnt);
+                                if (w <= 0) { cerr << "Error: write failed" << endl; exit(-1); }
+                                off += (uint64_t)w;
+                                while (w > 0 && first < iov.size()) { // advance over what was written
+                                    if ((size_t)w >= iov[first].iov_len) { w -= (ssize_t)iov[first].iov_len; ++first; }
+                                    else { iov[first].iov_base = (char *)iov[first].iov_base + w; iov[first].iov_len -= (size_t)w; w = 0; }
+                                }
+                            }
+                            iov.clear();
+                        };
+                        auto add = [&](const void *ptr, size_t n) { iov.push_back({(void *)ptr, n}); };
+                        for (size_t i = cut[(size_t)k]; i < cut[(size_t)k + 1]; ++i) {
+                            const Emit &e = emits[i];
+                            const uint8_t *sq = b.bases.data() + b.offsets[e.read] + e.start;
+                            if (iov.size() + 7 > 1024) flush();
+                            add(P.Outfq == 1 ? &kAt : &kGt, 1);
+                            add(nm[i]->data(), nm[i]->size());
+                            add(&kNl, 1);
+                            add(sq, e.len);
+                            if (P.Outfq == 1) {
+                                add(kPlus, 3);
+                                add(b.quals.data() + b.offsets[e.read] + e.start, e.len);
+                            }
+                            add(&kNl, 1);
+                        }
+                        flush();
+                    };
+                    std::vector<std::thread> th;
+                    for (int k = 1; k < K; ++k) th.emplace_back(write_range, k);
+                    write_range(0);
+                    for (auto &t : th) t.join();
+                    out_off += bytes_before[(size_t)K];
+                }
+            }
+            batch_pool.put(std::move(job->rb));
+        }
+    });
+
+    std::vector<tgsf_read_result> rr;
     auto retire = [&]() {
         const int bi = inflight.front();
         inflight.pop_front();
-        Batch &b = ring[(size_t)bi];
+        PinSlot &sl = ring[(size_t)bi];
         tgsf_ctx *c = ctx[(size_t)(bi % P.gpus)];
-        rr.resize(b.n());
-        pc.resize((size_t)b.n() + 4096);
+        const uint32_t n = sl.rb->n();
+        std::unique_ptr<WriteJob> job(new WriteJob());
+        rr.resize(n);
+        job->pieces.resize((size_t)n + 4096);
         uint32_t np = 0;
-        int rc = tgsf_collect(c, rr.data(), b.n(), pc.data(), (uint32_t)pc.size(), &np);
-        if (rc == TGSF_ERR_CAPACITY && np > pc.size()) {
-            pc.resize(np);
-            rc = tgsf_collect(c, rr.data(), b.n(), pc.data(), (uint32_t)pc.size(), &np);
+        int rc = tgsf_collect(c, rr.data(), n, job->pieces.data(), (uint32_t)job->pieces.size(), &np);
+        if (rc == TGSF_ERR_CAPACITY && np > job->pieces.size()) {
+            job->pieces.resize(np);
+            rc = tgsf_collect(c, rr.data(), n, job->pieces.data(), (uint32_t)job->pieces.size(), &np);
         }
         if (rc != TGSF_OK) die_tgsf("tgsf_collect");
-        uint32_t last = UINT32_MAX;
-        int pass = 1;
-        string rec, gz;
-        for (uint32_t i = 0; i < np; i++) { // T.cpp:1976-2059
-            const tgsf_piece &p = pc[i];
-            if ((uint32_t)p.read != last) { last = (uint32_t)p.read; pass = 1; }
-            if (p.status != TGSF_PIECE_EMIT) continue;
-            const string &raw = b.names[last];
-            const string name = pass >= 2 ? new_seq_name(raw, pass) : raw;
-            pass++;
-            const char *s = (const char *)b.bases.data() + b.offsets[last] + p.start;
-            rec.clear();
-            if (P.Outfq == 1) {
-                const char *q = (const char *)b.quals + b.offsets[last] + p.start;
-                rec += '@'; rec += name; rec += '\n'; rec.append(s, p.len); rec += "\n+\n"; rec.append(q, p.len); rec += '\n';
-            } else {
-                rec += '>'; rec += name; rec += '\n'; rec.append(s, p.len); rec += '\n';
-            }
-            if (gz_now) {
-                if (gz_member(rec, P.compLevel, gz)) fwrite(gz.data(), 1, gz.size(), out);
-            } else {
-                fwrite(rec.data(), 1, rec.size(), out);
-            }
-            if (P.Downsample) {
-                recIdx.add(name, p.len);
-                recSlot.push_back(recIdx.pos[name]);
-                recSpan.emplace_back(tmpBytes, (uint32_t)rec.size());
-                tmpBytes += rec.size();
-            }
-            cleanNum++;
-            cleanBases += (uint64_t)p.len;
-            cleanLens.push_back(p.len);
-        }
-        b.clear();
+        job->pieces.resize(np);
+        job->rb = std::move(sl.rb);
+        to_write.push(std::move(job));
     };
-    auto submit = [&](int bi) {
-        Batch &b = ring[(size_t)bi];
-        tgsf_ctx *c = ctx[(size_t)(bi % P.gpus)];
-        if (!b.pack()) die_tgsf("tgsf_pack_bases");
-        if (tgsf_submit_packed(c, b.packed, has_qual ? b.quals : nullptr, b.offsets.data(), b.n(), b.exc_pos.data(),
-                               b.exc_byte.data(), b.n_exc) != TGSF_OK)
+    int cur = 0;
+    double t_wait_in = 0, t_pack = 0, t_copy = 0, t_submit = 0, t_retire = 0;
+    Timer T_loop;
+    while (true) {
+        std::unique_ptr<ingest::RawBatch> rb;
+        T_loop.lap();
+        if (!pending.empty()) { rb = std::move(pending.front()); pending.pop_front(); }
+        else if (!input_done) { rb = next_parsed(); if (!rb) input_done = true; }
+        if (!rb) break;
+        t_wait_in += T_loop.lap();
+        const uint32_t n = rb->n();
+        const uint64_t nb = rb->bases.size();
+        rawNum += n;
+        rawBases += nb;
+        for (uint32_t i = 0; i < n; i++) rawLens.push_back((int)(rb->offsets[i + 1] - rb->offsets[i]));
+        T_loop.lap();
+        if ((int)inflight.size() == slots) retire(); // ring slot `cur` is the oldest one in flight
+        t_retire += T_loop.lap();
+        PinSlot &sl = ring[(size_t)cur];
+        if (!sl.reserve((size_t)nb + 64)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
+        uint64_t ne = 0;
+        sl.exc_pos.resize(std::max<size_t>(sl.exc_pos.size(), 1024));
+        sl.exc_byte.resize(sl.exc_pos.size());
+        int rc = tgsf_pack_bases(rb->bases.data(), nb, sl.packed, sl.exc_pos.data(), sl.exc_byte.data(), sl.exc_pos.size(), &ne);
+        if (rc == TGSF_ERR_CAPACITY) {
+            sl.exc_pos.resize(ne);
+            sl.exc_byte.resize(ne);
+            rc = tgsf_pack_bases(rb->bases.data(), nb, sl.packed, sl.exc_pos.data(), sl.exc_byte.data(), sl.exc_pos.size(), &ne);
+        }
+        if (rc != TGSF_OK) die_tgsf("tgsf_pack_bases");
+        t_pack += T_loop.lap();
+        if (has_qual && nb) memcpy(sl.quals, rb->quals.data(), nb);
+        t_copy += T_loop.lap();
+        if (tgsf_submit_packed(ctx[(size_t)(cur % P.gpus)], sl.packed, has_qual ? sl.quals : nullptr, rb->offsets.data(), n,
+                               sl.exc_pos.data(), sl.exc_byte.data(), ne) != TGSF_OK)
             die_tgsf("tgsf_submit_packed");
-        inflight.push_back(bi);
-        submitted++;
-    };
-    {
-        FastxReader rd(P.InFile);
-        string name, seq, qual;
-        int cur = 0;
-        while (rd.read(name, seq, qual)) {
-            rawNum++;
-            rawBases += seq.size();
-            rawLens.push_back((int)seq.size());
-            Batch &b = ring[(size_t)cur];
-            if (!b.add(name, seq, qual, has_qual)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
-            if (b.used >= P.batch_bases) {
-                submit(cur);
-                cur = (cur + 1) % slots;
-                if ((int)inflight.size() == slots) retire(); // the ring slot we are about to fill is free again
-            }
-        }
-        if (ring[(size_t)cur].n()) submit(cur);
-        while (!inflight.empty()) retire();
+        t_submit += T_loop.lap();
+        sl.rb = std::move(rb);
+        inflight.push_back(cur);
+        cur = (cur + 1) % slots;
     }
+    T_loop.lap();
+    while (!inflight.empty()) retire();
+    t_retire += T_loop.lap();
+    to_write.push(nullptr);
+    writer.join();
+    tlog("main loop: wait for parsed input", t_wait_in); tlog("main loop: reserve+pack", t_pack); tlog("main loop: quals memcpy", t_copy);
+    tlog("main loop: submit", t_submit); tlog("main loop: collect/retire", t_retire); tlog("writer join", T_loop.lap());
+    tlog("main pass total", T_ph.lap());
+    if (reader.joinable()) {
+        while (!input_done) { if (!next_parsed()) input_done = true; } // drain (only after an early error)
+        reader.join();
+    }
+    if (clean_exit) for (PinSlot &sl : ring) { tgsf_host_free(sl.packed); tgsf_host_free(sl.quals); }
     if (out != stdout) fclose(out);
 
     // ---- counters: merge over GPUs (T.cpp:3208-3213) and the INFO lines (T.cpp:3214-3235) ----------
@@ -763,8 +996,7 @@ int main(int argc, char **argv) {
             fclose(f);
         }
     }
-    for (Batch &b : ring) b.release();
-    for (tgsf_ctx *c : ctx) tgsf_destroy(c);
+    if (clean_exit) for (tgsf_ctx *c : ctx) tgsf_destroy(c);
     }
 
     // ---- downsampling: DownSampleTask (T.cpp:2164-2568) -------------------------------------------
@@ -846,6 +1078,7 @@ int main(int argc, char **argv) {
         if (!tmpPath.empty()) remove(tmpPath.c_str());
     }
 
+    tlog("counters/info/downsample", T_ph.lap());
     // ---- QC report (T.cpp:3285-3328) -----------------------------------------------------------------
     {
         auto prefix_of = [](const string &path) { // GetFilePreifx, T.cpp:824-837
@@ -864,5 +1097,12 @@ int main(int argc, char **argv) {
         report::write_html(html, qcType, rawSide, cleanSide);
         cerr << "INFO: Quality control report was written to: " << html << "." << endl;
     }
-    return 0;
+    tlog("report", T_ph.lap());
+    tlog("total", T_all.lap());
+    if (clean_exit) return 0;
+    // everything is written: leave without tearing down GBs of device, pinned and batch memory piece by piece
+    std::cout.flush();
+    cerr.flush();
+    fflush(nullptr);
+    _exit(0);
 }

@@ -1,0 +1,397 @@
+// Host ingest pipeline of the tgsfilter host: a reader thread parses
+// FASTQ/FASTA (plain or gzip, through zlib) straight out of a large read buffer into variable-length
+// batches, the main thread feeds the GPUs, a writer thread formats and writes the records.  Replaces
+// the reference's 1 reader + N workers + 1 writer joined by 1 ms-sleep polling (T.cpp:1808-1916).
+//
+// The parser follows FastxReader's record rules (T.cpp:685-760): 4-line FASTQ / 2-line FASTA, a
+// record starts at the next line beginning with '@' / '>', '\r' before '\n' is dropped, an empty or
+// length-mismatched quality line stops the input with the reference's message.
+#pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstring>
+#include <deque>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace ingest {
+
+struct RawBatch { // pageable; the byte bases stay here for record output
+    std::vector<uint8_t> bases, quals;
+    std::vector<uint64_t> offsets{0};
+    std::vector<std::string> names;
+    uint32_t n() const { return (uint32_t)names.size(); }
+};
+
+template <typename T>
+class Queue { // bounded blocking queue
+public:
+    explicit Queue(size_t cap) : cap_(cap) {}
+    void push(T v) {
+        std::unique_lock<std::mutex> lk(m_);
+        not_full_.wait(lk, [&] { return q_.size() < cap_; });
+        q_.push_back(std::move(v));
+        not_empty_.notify_one();
+    }
+    T pop() {
+        std::unique_lock<std::mutex> lk(m_);
+        not_empty_.wait(lk, [&] { return !q_.empty(); });
+        T v = std::move(q_.front());
+        q_.pop_front();
+        not_full_.notify_one();
+        return v;
+    }
+
+private:
+    size_t cap_;
+    std::mutex m_;
+    std::condition_variable not_full_, not_empty_;
+    std::deque<T> q_;
+};
+
+class FastParser {
+public:
+    FastParser(const std::string &path, bool fastq) : fastq_(fastq) {
+        // plain files are read with read(2) straight into the parse buffer; gzip goes through zlib
+        FILE *probe = fopen(path.c_str(), "rb");
+        unsigned char magic[2] = {0, 0};
+        const bool gz = probe && fread(magic, 1, 2, probe) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (probe) fclose(probe);
+        if (gz) {
+            f_ = gzopen(path.c_str(), "rb");
+            if (f_) gzbuffer(f_, 1 << 20);
+        } else {
+            fd_ = open(path.c_str(), O_RDONLY);
+        }
+        buf_.resize(8u << 20);
+    }
+    ~FastParser() {
+        if (f_) gzclose(f_);
+        if (fd_ >= 0) close(fd_);
+    }
+    bool ok() const { return f_ != nullptr || fd_ >= 0; }
+
+    struct Rec { const char *name, *seq, *qual; size_t name_len, seq_len, qual_len; };
+
+    // Views stay valid until the next call.  false: end of input (or a malformed record).
+    bool next(Rec &r) {
+        while (true) {
+            size_t p = pos_, lp[4] = {0, 0, 0, 0}, ln[4] = {0, 0, 0, 0};
+            int rc = line_at(p, lp[0], ln[0]);
+            if (rc == 0) { refill(); continue; }
+            if (rc < 0) return false;
+            if (ln[0] == 0 || buf_[lp[0]] != (fastq_ ? '@' : '>')) { pos_ = p; continue; } // resynchronise
+            const int need = fastq_ ? 4 : 2;
+            int got = 1;
+            for (; got < need; ++got) {
+                rc = line_at(p, lp[got], ln[got]);
+                if (rc <= 0) break;
+            }
+            if (got < need) {
+                if (rc == 0) { refill(); continue; } // restart this record with more data
+                return false;                         // truncated trailing record
+            }
+            if (fastq_ && (ln[2] == 0 || buf_[lp[2]] != '+' || ln[1] == 0)) {
+                // header without a valid body: the reference goes on from the line after the '+' slot
+                size_t q = pos_, a = 0, b = 0;
+                for (int i = 0; i < 3; ++i) line_at(q, a, b);
+                pos_ = q;
+                continue;
+            }
+            pos_ = p;
+            r.name = buf_.data() + lp[0] + 1;
+            r.name_len = ln[0] - 1;
+            r.seq = buf_.data() + lp[1];
+            r.seq_len = ln[1];
+            if (fastq_) {
+                r.qual = buf_.data() + lp[3];
+                r.qual_len = ln[3];
+                if (r.qual_len == 0) {
+                    std::cerr << "Error: quality are empty:" << std::string(r.name, r.name_len) << std::endl;
+                    return false;
+                }
+                if (r.qual_len != r.seq_len) {
+                    std::cerr << "warning: sequence and quality have different length:" << std::string(r.name, r.name_len) << std::endl;
+                    return false;
+                }
+            } else {
+                r.qual = nullptr;
+                r.qual_len = 0;
+                if (r.seq_len == 0) {
+                    std::cerr << "Error: sequence are empty:" << std::string(r.name, r.name_len) << std::endl;
+                    return false;
+                }
+            }
+            return true;
+        }
+    }
+
+private:
+    // Line starting at p: [lp, lp+n) without its terminator; advances p.  1 = line, 0 = incomplete
+    // (more input needed), -1 = end of data.  At EOF an unterminated tail counts as a line.
+    int line_at(size_t &p, size_t &lp, size_t &n) {
+        if (p >= len_) return eof_ ? -1 : 0;
+        const char *s = buf_.data() + p;
+        const char *nl = (const char *)memchr(s, '\n', len_ - p);
+        lp = p;
+        if (!nl) {
+            if (!eof_) return 0;
+            n = len_ - p;
+            p = len_;
+        } else {
+            n = (size_t)(nl - s);
+            p += n + 1;
+        }
+        if (n && buf_[lp + n - 1] == '\r') --n;
+        return 1;
+    }
+    void refill() {
+        if (pos_ > 0) {
+            memmove(buf_.data(), buf_.data() + pos_, len_ - pos_);
+            len_ -= pos_;
+            pos_ = 0;
+        }
+        if (len_ == buf_.size()) buf_.resize(buf_.size() * 2); // one record larger than the buffer
+        while (len_ < buf_.size()) {
+            const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
+            const long got = f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want) : (long)read(fd_, buf_.data() + len_, want);
+            if (got <= 0) { eof_ = true; break; }
+            len_ += (size_t)got;
+            if (len_ >= buf_.size() / 2) break;
+        }
+    }
+    gzFile f_ = nullptr;
+    int fd_ = -1;
+    bool fastq_, eof_ = false;
+    std::vector<char> buf_;
+    size_t pos_ = 0, len_ = 0;
+};
+
+// Reader thread body: parse the whole file into batches of ~batch_bases bases; nullptr ends the stream.
+// Recycled RawBatch buffers (touched pages are expensive to fault in again for every batch).
+class BatchPool {
+public:
+    std::unique_ptr<RawBatch> get() {
+        std::lock_guard<std::mutex> lk(m_);
+        if (free_.empty()) return std::unique_ptr<RawBatch>(new RawBatch());
+        std::unique_ptr<RawBatch> b = std::move(free_.back());
+        free_.pop_back();
+        return b;
+    }
+    void put(std::unique_ptr<RawBatch> b) {
+        b->bases.clear();
+        b->quals.clear();
+        b->offsets.assign(1, 0);
+        b->names.clear();
+        std::lock_guard<std::mutex> lk(m_);
+        if (free_.size() < 32) free_.push_back(std::move(b));
+    }
+
+private:
+    std::mutex m_;
+    std::vector<std::unique_ptr<RawBatch>> free_;
+};
+
+inline void reader_main(const std::string &path, bool fastq, uint64_t batch_bases,
+                        Queue<std::unique_ptr<RawBatch>> *out, BatchPool *pool) {
+    FastParser ps(path, fastq);
+    auto fresh = [&]() {
+        std::unique_ptr<RawBatch> nb = pool->get();
+        nb->bases.reserve((size_t)batch_bases + (batch_bases >> 2));
+        if (fastq) nb->quals.reserve((size_t)batch_bases + (batch_bases >> 2));
+        return nb;
+    };
+    std::unique_ptr<RawBatch> b = fresh();
+    FastParser::Rec r;
+    while (ps.ok() && ps.next(r)) {
+        b->names.emplace_back(r.name, r.name_len);
+        b->bases.insert(b->bases.end(), (const uint8_t *)r.seq, (const uint8_t *)r.seq + r.seq_len);
+        if (fastq) b->quals.insert(b->quals.end(), (const uint8_t *)r.qual, (const uint8_t *)r.qual + r.qual_len);
+        b->offsets.push_back(b->bases.size());
+        if (b->bases.size() >= batch_bases) {
+            out->push(std::move(b));
+            b = fresh();
+        }
+    }
+    if (b->n()) out->push(std::move(b));
+    out->push(nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Parallel ingest of plain (uncompressed) files: the file is mmap'ed and cut into ~64 MB chunks at
+// record boundaries; worker threads parse chunks independently, the consumer receives the batches
+// in file order.  A FASTQ record start is a line beginning with '@' whose second-next line begins
+// with '+' (exact for well-formed 4-line FASTQ: a quality line that happens to start with '@' is
+// followed by a header and a base line, never by a '+' line two below); FASTA: a line beginning
+// with '>'.  gzip input keeps the single-reader path (inflate is serial).
+// ---------------------------------------------------------------------------------------------
+class ParallelReader {
+public:
+    ParallelReader(const std::string &path, bool fastq, uint64_t chunk_bytes, int threads, BatchPool *pool)
+        : fastq_(fastq), chunk_(chunk_bytes), pool_(pool) {
+        fd_ = open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd_ < 0 || fstat(fd_, &st) != 0) return;
+        size_ = (size_t)st.st_size;
+        if (size_ == 0) { ok_ = true; n_chunks_ = 0; return; }
+        void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+        if (m == MAP_FAILED) return;
+        base_ = (const char *)m;
+        madvise((void *)base_, size_, MADV_SEQUENTIAL);
+        n_chunks_ = (size_ + chunk_ - 1) / chunk_;
+        slots_.resize(n_chunks_);
+        ready_.assign(n_chunks_, 0);
+        window_ = (size_t)std::max(4, 3 * threads);
+        ok_ = true;
+        for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { work(); });
+    }
+    ~ParallelReader() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+        if (base_) munmap((void *)base_, size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    bool ok() const { return ok_; }
+    static bool is_gzip(const std::string &path) {
+        FILE *f = fopen(path.c_str(), "rb");
+        unsigned char m[2] = {0, 0};
+        const bool gz = f && fread(m, 1, 2, f) == 2 && m[0] == 0x1f && m[1] == 0x8b;
+        if (f) fclose(f);
+        return gz;
+    }
+    // next batch in file order; nullptr at the end (or after a malformed record)
+    std::unique_ptr<RawBatch> pop() {
+        std::unique_lock<std::mutex> lk(m_);
+        while (true) {
+            if (failed_ || next_out_ >= n_chunks_) return nullptr;
+            cv_.wait(lk, [&] { return ready_[next_out_] != 0; });
+            std::unique_ptr<RawBatch> b = std::move(slots_[next_out_]);
+            const bool bad = ready_[next_out_] == 2;
+            ++next_out_;
+            cv_.notify_all();
+            if (bad) failed_ = true; // the records before the malformed one are still delivered
+            if (b && b->n()) return b;
+            if (bad) return nullptr;
+        }
+    }
+
+private:
+    // first record start at or after `from` (from == 0: the file start)
+    size_t record_start(size_t from) const {
+        if (from == 0) return 0;
+        if (from >= size_) return size_;
+        const char *p = (const char *)memchr(base_ + from - 1, '\n', size_ - from + 1);
+        if (!p) return size_;
+        size_t pos = (size_t)(p - base_) + 1;
+        const char hdr = fastq_ ? '@' : '>';
+        while (pos < size_) {
+            if (base_[pos] == hdr) {
+                if (!fastq_) return pos;
+                // line + 2 must start with '+'
+                const char *l1 = (const char *)memchr(base_ + pos, '\n', size_ - pos);
+                if (!l1) return size_;
+                const char *l2 = (const char *)memchr(l1 + 1, '\n', size_ - (size_t)(l1 + 1 - base_));
+                if (!l2) return size_;
+                if ((size_t)(l2 + 1 - base_) < size_ && l2[1] == '+') return pos;
+            }
+            const char *nl = (const char *)memchr(base_ + pos, '\n', size_ - pos);
+            if (!nl) return size_;
+            pos = (size_t)(nl - base_) + 1;
+        }
+        return size_;
+    }
+    static inline bool get_line(const char *&p, const char *e, const char *&ls, size_t &n) {
+        if (p >= e) return false;
+        const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+        ls = p;
+        if (nl) { n = (size_t)(nl - p); p = nl + 1; }
+        else { n = (size_t)(e - p); p = e; }
+        if (n && ls[n - 1] == '\r') --n;
+        return true;
+    }
+    // parse [s, e) (record aligned); false on a malformed record (same messages as the serial parser)
+    bool parse_range(const char *s, const char *e, RawBatch &b) const {
+        const char *p = s;
+        const char hdr = fastq_ ? '@' : '>';
+        while (p < e) {
+            const char *l0, *l1, *l2, *l3;
+            size_t n0, n1, n2 = 0, n3 = 0;
+            const char *save = p;
+            if (!get_line(p, e, l0, n0)) break;
+            if (n0 == 0 || l0[0] != hdr) continue; // resynchronise
+            if (!get_line(p, e, l1, n1)) break;
+            if (fastq_) {
+                if (!get_line(p, e, l2, n2) || !get_line(p, e, l3, n3)) break;
+                if (n2 == 0 || l2[0] != '+' || n1 == 0) { // header without a valid body
+                    p = save;
+                    for (int i = 0; i < 3; ++i) get_line(p, e, l0, n0);
+                    continue;
+                }
+                if (n3 == 0) { std::cerr << "Error: quality are empty:" << std::string(l0 + 1, n0 - 1) << std::endl; return false; }
+                if (n3 != n1) { std::cerr << "warning: sequence and quality have different length:" << std::string(l0 + 1, n0 - 1) << std::endl; return false; }
+                b.quals.insert(b.quals.end(), (const uint8_t *)l3, (const uint8_t *)l3 + n3);
+            } else if (n1 == 0) {
+                std::cerr << "Error: sequence are empty:" << std::string(l0 + 1, n0 - 1) << std::endl;
+                return false;
+            }
+            b.names.emplace_back(l0 + 1, n0 - 1);
+            b.bases.insert(b.bases.end(), (const uint8_t *)l1, (const uint8_t *)l1 + n1);
+            b.offsets.push_back(b.bases.size());
+        }
+        return true;
+    }
+    void work() {
+        while (true) {
+            size_t ci;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || failed_ || next_in_ >= n_chunks_ || next_in_ < next_out_ + window_; });
+                if (stop_ || failed_ || next_in_ >= n_chunks_) return;
+                ci = next_in_++;
+            }
+            const size_t s = record_start(ci * chunk_), e = record_start((ci + 1) * chunk_);
+            std::unique_ptr<RawBatch> b = pool_->get();
+            bool good = true;
+            if (e > s) {
+                b->bases.reserve((e - s) / 2 + 1024);
+                if (fastq_) b->quals.reserve((e - s) / 2 + 1024);
+                good = parse_range(base_ + s, base_ + e, *b);
+            }
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                slots_[ci] = std::move(b);
+                ready_[ci] = good ? 1 : 2;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    bool fastq_, ok_ = false, stop_ = false, failed_ = false;
+    uint64_t chunk_;
+    BatchPool *pool_;
+    int fd_ = -1;
+    const char *base_ = nullptr;
+    size_t size_ = 0, n_chunks_ = 0, next_in_ = 0, next_out_ = 0, window_ = 8;
+    std::vector<std::unique_ptr<RawBatch>> slots_;
+    std::vector<char> ready_;
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable cv_;
+};
+
+}  // namespace ingest

@@ -575,3 +575,45 @@ def test_host_cli_downsample_report_vs_reference(args):
     h_data, h_cells = _report_parts(h_html)
     assert h_cells == r_cells
     assert h_data == r_data
+
+
+def _repeat_batch(seed, n=48, long_read=0):
+    """Reads with tandem repeats, N / lower-case bytes and odd lengths; optionally one read long enough
+    to need several staged tiles in the shared-memory k-mer kernel (> 196 608 bases)."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for i in range(n):
+        L = int(rng.integers(60, 9000))
+        parts, have = [], 0
+        while have < L:
+            if rng.random() < 0.5:
+                unit = acgt[rng.integers(0, 4, int(rng.integers(1, 40)))]
+                seg = np.tile(unit, int(rng.integers(2, 60)))
+            else:
+                seg = acgt[rng.integers(0, 4, int(rng.integers(20, 800)))]
+            parts.append(seg)
+            have += len(seg)
+        s = np.concatenate(parts)[:L].copy()
+        if i % 3 == 0:
+            s[rng.integers(0, L, max(1, L // 40))] = np.frombuffer(b"Nacgt", dtype=np.uint8)[rng.integers(0, 5, max(1, L // 40))]
+        seqs.append(s.tobytes())
+    if long_read:
+        unit = acgt[rng.integers(0, 4, 70001)]
+        seqs.insert(3, np.concatenate([np.tile(unit, long_read // 70001 + 1)[:long_read]]).tobytes())
+    quals = [bytes([40 + 33]) * len(s) for s in seqs]
+    return synth.pack_reads(seqs, quals)
+
+
+@pytest.mark.parametrize("k", [2, 5, 8, 10, 11, 12, 13, 14, 16, 21, 31])
+def test_kmer_repeat_length_on_every_kernel_path(k, monkeypatch):
+    """GetKmerCount (T.cpp:1703-1753): shared-memory bitmap passes (k <= 12), global bitmap (13),
+    hash sets (> 13); -p drops pieces whose repeat length is below the bound."""
+    batch = _repeat_batch(100 + k, long_read=450000 if k in (5, 11, 12) else 0)
+    params = FilterParams(min_len=50, min_q=0.0, kmer=k, min_repeat=200, qtype=33, adapters=[],
+                          max_read_len=500000)
+    r, p, _ = _compare(params, batch)
+    assert (p["status"] != 0).any() and (p["status"] == 0).any()
+    if k in (8, 11):  # the global-memory bitmap kernel on the same input
+        monkeypatch.setenv("TGSF_KMER_L2", "1")
+        _compare(params, batch)

@@ -233,10 +233,12 @@ def test_world_size_2_counters_allreduce_equals_single_process():
 def test_pack_bases_roundtrip_on_cpu():
     lib = _capi.load()
     rng = np.random.default_rng(2)
-    for n in (0, 1, 3, 4, 5, 1000, 4099):
+    for n in (0, 1, 3, 4, 5, 31, 32, 33, 63, 64, 65, 1000, 4099, 100003):  # 32-base SIMD groups + scalar tails
         b = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
         if n > 10:
             b[rng.integers(0, n, 7)] = np.frombuffer(b"NacgtRY", dtype=np.uint8)
+        if n > 100:
+            b[[31, 32, 64, n - 1]] = ord("N")  # group edges
         packed = np.zeros((n + 3) // 4 + 1, dtype=np.uint8)
         pos = np.zeros(16, dtype=np.uint64)
         val = np.zeros(16, dtype=np.uint8)
@@ -254,3 +256,40 @@ def test_pack_bases_roundtrip_on_cpu():
     ne = C.c_uint64(0)
     assert lib.tgsf_pack_bases(b.ctypes.data, 8, packed.ctypes.data, None, None, 0, C.byref(ne)) == _capi.TGSF_ERR_CAPACITY
     assert ne.value == 8
+
+
+def _write_fastx(path, n, fastq, crlf, rng):
+    nl = b"\r\n" if crlf else b"\n"
+    with open(path, "wb") as f:
+        for i in range(n):
+            ln = int(rng.integers(1, 2000))
+            s = rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), ln).tobytes()
+            # qualities 33..74 include '@' and '+', so quality lines may start with either
+            q = rng.integers(33, 75, ln).astype(np.uint8).tobytes()
+            f.write((b"@r%d x" % i + nl + s + nl + b"+" + nl + q + nl) if fastq else (b">r%d" % i + nl + s + nl))
+
+
+@pytest.mark.parametrize("fastq", [1, 0])
+def test_parallel_chunk_parser_equals_serial_reader(tmp_path, fastq):
+    """src/pipeline.hpp: record-boundary sync + ordered delivery of the parallel ingest equal the
+    serial FastxReader-rule parser (T.cpp:685-760) on files whose quality lines start with '@'."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "ingest_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(17 + fastq)
+    for crlf in (False, True):
+        path = str(tmp_path / ("in_%d.fx" % crlf))
+        _write_fastx(path, 1500, bool(fastq), crlf, rng)
+        for chunk, thr in ((700, 3), (40000, 2), (1 << 22, 4)):
+            r = subprocess.run([exe, path, str(fastq), str(chunk), str(thr)], capture_output=True, text=True)
+            assert r.returncode == 0, (crlf, chunk, thr, r.stdout, r.stderr)
+            assert r.stdout.split()[0] == "1500"
+    # unterminated last line and an empty file
+    tail = str(tmp_path / "tail.fq")
+    open(tail, "wb").write(b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII")
+    assert subprocess.run([exe, tail, "1", "7", "2"], capture_output=True).returncode == 0
+    empty = str(tmp_path / "empty.fq")
+    open(empty, "wb").close()
+    assert subprocess.run([exe, empty, "1", "64", "2"], capture_output=True).returncode == 0

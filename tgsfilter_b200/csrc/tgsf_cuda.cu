@@ -219,6 +219,7 @@ struct tgsf_ctx {
     std::vector<Slot> slots;
     u32 head = 0, tail = 0, outstanding = 0; // ring: submit at head, collect at tail
     u64 launches = 0;
+    bool kmer_force_l2 = false; // TGSF_KMER_L2=1: keep k <= 12 on the global-memory bitmap kernel (A/B, tests)
     float last_kernel_ms = 0, last_total_ms = 0;
     float last_stage_ms[TGSF_N_STAGES] = {};
 };
@@ -566,7 +567,12 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
     c->launches++;
     CU(cudaEventRecord(s.ev_stage[5], st));
     if (!(P.flags & TGSF_FLAG_ONLY_QC)) {
-        if (P.min_repeat > 0 && P.kmer <= 13) {
+        if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2) {
+            // shared-memory bitmap in key-range passes
+            k_kmer_smem<<<c->sm_count, KMER_SB_THREADS, KMER_SB_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
+                                                                                 &H->tmp_cursor, C, &H->status);
+            c->launches++;
+        } else if (P.min_repeat > 0 && P.kmer <= 13) {
             // bitmap path: one 4^k-bit map per CTA, zeroed once and kept clean by the kernel
             const u64 words = (1ull << (2 * P.kmer)) / 32 + 1;
             const int grid = P.kmer <= 11 ? c->sm_count : std::max(1, c->sm_count / (1 << (2 * (P.kmer - 11))));
@@ -728,8 +734,10 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
     if (rc == TGSF_OK) {
         cudaError_t e1 = cudaFuncSetAttribute(k_scan_tiles_dyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(k_scan_tiles_dyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
+        c->kmer_force_l2 = getenv("TGSF_KMER_L2") != nullptr;
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
+        if (e4 == cudaSuccess) e4 = cudaFuncSetAttribute(k_kmer_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SB_SMEM_BYTES);
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
             set_err("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4));
             rc = TGSF_ERR_CUDA;
@@ -852,13 +860,18 @@ int tgsf_submit_packed(tgsf_ctx *c, const uint8_t *packed_bases, const uint8_t *
     return submit_common(c, nullptr, quals, (const u64 *)offsets, n_reads, n_bases, false, &pk);
 }
 
+extern "C" int tgsf_pack_has_avx2();
+extern "C" uint64_t tgsf_pack_groups_avx2(const uint8_t *bases, uint8_t *packed, uint64_t g0, uint64_t n_groups);
+
 int tgsf_pack_bases(const uint8_t *bases, uint64_t n, uint8_t *packed, uint64_t *exc_pos, uint8_t *exc_byte,
                     uint64_t exc_cap, uint64_t *n_exc) {
     if ((n && (!bases || !packed)) || !n_exc) { set_err("pack: NULL argument"); return TGSF_ERR_INVALID; }
     static const struct Lut { uint8_t code[256]; Lut() { memset(code, 4, 256); code['A'] = 0; code['C'] = 1; code['G'] = 2; code['T'] = 3; } } lut;
     u64 ne = 0;
     const u64 full = n / 4;
-    for (u64 i = 0; i < full; ++i) {
+    static const bool avx2 = tgsf_pack_has_avx2() != 0;
+    const u64 groups = avx2 ? n / 32 : 0; // 32 bases = 8 packed bytes per AVX2 step (pack_host.cpp)
+    auto scalar_word = [&](u64 i) {
         const uint8_t c0 = lut.code[bases[4 * i]], c1 = lut.code[bases[4 * i + 1]], c2 = lut.code[bases[4 * i + 2]],
                       c3 = lut.code[bases[4 * i + 3]];
         if ((c0 | c1 | c2 | c3) & 4) { // rare: at least one byte is not upper-case ACGT
@@ -876,6 +889,19 @@ int tgsf_pack_bases(const uint8_t *bases, uint64_t n, uint8_t *packed, uint64_t 
         } else {
             packed[i] = (uint8_t)(c0 | (c1 << 2) | (c2 << 4) | (c3 << 6));
         }
+    };
+    u64 i = 0;
+    while (i < full) {
+        if ((i & 7) == 0 && (i >> 3) < groups) {
+            const u64 g = tgsf_pack_groups_avx2(bases, packed, i >> 3, groups);
+            i = g << 3;
+            if (g < groups) { // group g holds an exception byte: its 8 words go through the scalar path
+                for (int w = 0; w < 8; ++w) scalar_word(i + (u64)w);
+                i += 8;
+            }
+            continue;
+        }
+        scalar_word(i++);
     }
     if (n & 3) {
         uint8_t v = 0;
