@@ -537,8 +537,10 @@ def main():
                 "peak": hbm_peak, "unit": "GB/s", "frac": clean_gbs / hbm_peak, "traffic": None,
                 "peak_source": hbm_src, "work": "2 B per kept base (upper bound: bases of reads passing -q/-Q)",
                 "ms": clean_ms, "share_of_step": clean_ms / step_ms if step_ms else None}
-    rl_kmer = {"kernel": "k_kmer_bitmap (K4, L2-resident 4^k-bit map per CTA; k > 13: shared-memory hash)",
-               "bound": "l2_atomics (one scattered atomicOr + one scattered clear per k-mer: L1tex wavefront rate)",
+    rl_kmer = {"kernel": "k_kmer_smem (K4, k <= 12: atomics-free tag rounds over a 2-bit staged piece in shared "
+                         "memory; pieces > 196 kb: shared-memory bitmap passes; k = 13: L2 bitmap; k > 13: hash)",
+               "bound": "issue+barrier (one CTA per piece: ~43 k warp-instructions and ~14 barriers per 15 kb piece; "
+                        "ncu: issue slots 52 % busy, 29 % of stall samples on barriers)",
                "achieved": kept_bases / (kmer_ms / 1e3) / 1e9 if kmer_ms > 0 else 0.0, "peak": None,
                "unit": "Ginserts/s", "frac": None, "traffic": None, "work": "1 insert per kept base",
                "ms": kmer_ms, "share_of_step": kmer_ms / step_ms if step_ms else None}

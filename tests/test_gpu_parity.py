@@ -607,13 +607,17 @@ def _repeat_batch(seed, n=48, long_read=0):
 
 @pytest.mark.parametrize("k", [2, 5, 8, 10, 11, 12, 13, 14, 16, 21, 31])
 def test_kmer_repeat_length_on_every_kernel_path(k, monkeypatch):
-    """GetKmerCount (T.cpp:1703-1753): shared-memory bitmap passes (k <= 12), global bitmap (13),
-    hash sets (> 13); -p drops pieces whose repeat length is below the bound."""
+    """GetKmerCount (T.cpp:1703-1753): k <= 12: tag rounds (piece fits one staged tile) or shared-memory
+    bitmap passes (longer pieces); global bitmap (13), hash sets (> 13); -p drops pieces whose repeat
+    length is below the bound."""
     batch = _repeat_batch(100 + k, long_read=450000 if k in (5, 11, 12) else 0)
     params = FilterParams(min_len=50, min_q=0.0, kmer=k, min_repeat=200, qtype=33, adapters=[],
                           max_read_len=500000)
     r, p, _ = _compare(params, batch)
     assert (p["status"] != 0).any() and (p["status"] == 0).any()
-    if k in (8, 11):  # the global-memory bitmap kernel on the same input
+    if k in (8, 11, 12):  # the other kernels for the same k on the same input
+        monkeypatch.setenv("TGSF_KMER_BITMAP", "1")
+        _compare(params, batch)
+        monkeypatch.delenv("TGSF_KMER_BITMAP")
         monkeypatch.setenv("TGSF_KMER_L2", "1")
         _compare(params, batch)

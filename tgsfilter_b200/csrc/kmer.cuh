@@ -178,14 +178,229 @@ static __device__ __forceinline__ u32 pack_codes4(u32 x) { // 4 bytes -> 8 bits,
     return (y * 0x40100401u) >> 24;
 }
 
+// Stage bases [abase, abase + 16 * n_words) as 2-bit codes into tile[0..n_words), tile[n_words] = 0.
+static __device__ __forceinline__ void kmer_stage_tile(const DevBatch &B, u64 n_total, u64 abase, u32 n_words, u32 *tile) {
+    for (u32 w = threadIdx.x; w < n_words + 1; w += blockDim.x) {
+        u32 v = 0;
+        if (w < n_words) {
+            const u64 a = abase + 16ull * w;
+            uint4 q;
+            if (a + 16 <= n_total) {
+                q = __ldg((const uint4 *)(B.bases + a));
+            } else { // last, partial group of the batch: bytes beyond the stream are not touched
+                __align__(16) uint8_t tmp[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) tmp[j] = (a + j < n_total) ? B.bases[a + j] : (uint8_t)0;
+                q = *(uint4 *)tmp;
+            }
+            v = (pack_codes4(q.x) << 24) | (pack_codes4(q.y) << 16) | (pack_codes4(q.z) << 8) | pack_codes4(q.w);
+        }
+        tile[w] = v; // tile[n_words] = 0: the window of the last word reads one word past it
+    }
+}
+
+// Atomics-free distinct count of the k-mers of ONE staged tile ("last writer wins" tags).
+// Shared-memory atomics run at ~2 cycles per lane per SM, plain shared stores at 32 lanes per cycle, so
+// the set is built without any read-modify-write: in each round every pending k-mer stores the tag
+// (remainder bits of its mixed key | its position) into slot = low 15 bits of the mixed key (a bijection
+// of the 2k-bit key, so slot + remainder identify the key exactly).  After a barrier each k-mer reads its
+// slot back: tag equal to its own -> it is the one representative of its key (count 1); same remainder ->
+// duplicate of the representative; otherwise its key lost the slot to another key and stays pending for
+// the next round (new multiplier).  All instances of a key share the slot and see the same winner, so
+// keys are resolved as a whole; a k-mer only reads a slot it has just written, so the table is never
+// cleared.  pend[w]: 16-bit mask of the unresolved positions of word w.
+#define KMER_TAG_SLOTS 32768u
+#define KMER_TAG_IDX_BITS 18
+static __device__ __forceinline__ u32 kmer_tag_of(u32 mixed, u32 pos) { // remainder bits above the position
+    return ((mixed << (KMER_TAG_IDX_BITS - 15)) & ~((1u << KMER_TAG_IDX_BITS) - 1u)) | pos;
+}
+
+static __device__ __forceinline__ u32 kmer_mix(u32 key, u32 mult, u32 keymask, u32 half) {
+    const u32 p = (key * mult) & keymask;
+    return p ^ (p >> half);
+}
+// x: 32 stream bits whose top 2k bits are the key.  Round 0 uses a plain xor-shift (a bijection of the key:
+// the bits shifted in from above are zero), later rounds a multiplicative mix with a per-round multiplier.
+template <bool R0>
+static __device__ __forceinline__ u32 kmer_mix_x(u32 x, u32 sh, u32 mult, u32 keymask, u32 half) {
+    if (R0) return (x ^ (x >> 11)) >> sh;
+    return kmer_mix(x >> sh, mult, keymask, half);
+}
+
+template <bool R0>
+static __device__ __forceinline__ void kmer_dense_store(const u32 *tile, u32 *table, const uint16_t *pend, u32 n_scan,
+                                                        u32 sh, u32 mult, u32 keymask, u32 half) {
+    for (u32 w = threadIdx.x; w < n_scan; w += blockDim.x) {
+        const u32 m = pend[w];
+        if (!m) continue;
+        const u32 w0 = tile[w], w1 = tile[w + 1], pw = w << 4;
+        if (m == 0xFFFFu) {
+#pragma unroll
+            for (u32 j = 0; j < 16; ++j) {
+                const u32 mixed = kmer_mix_x<R0>(__funnelshift_l(w1, w0, 2 * j), sh, mult, keymask, half);
+                table[mixed & (KMER_TAG_SLOTS - 1)] = kmer_tag_of(mixed, pw + j);
+            }
+        } else {
+#pragma unroll 4
+            for (u32 j = 0; j < 16; ++j) {
+                if ((m >> j) & 1u) {
+                    const u32 mixed = kmer_mix_x<R0>(__funnelshift_l(w1, w0, 2 * j), sh, mult, keymask, half);
+                    table[mixed & (KMER_TAG_SLOTS - 1)] = kmer_tag_of(mixed, pw + j);
+                }
+            }
+        }
+    }
+}
+
+// returns (#representatives found by this thread) and adds its still-pending count to `left`
+template <bool R0>
+static __device__ __forceinline__ u32 kmer_dense_read(const u32 *tile, const u32 *table, uint16_t *pend, u32 n_scan, u32 sh,
+                                                      u32 mult, u32 keymask, u32 half, u32 &left) {
+    u32 mine = 0;
+    for (u32 w = threadIdx.x; w < n_scan; w += blockDim.x) {
+        u32 m = pend[w];
+        if (!m) continue;
+        const u32 w0 = tile[w], w1 = tile[w + 1], pw = w << 4;
+        if (m == 0xFFFFu) {
+#pragma unroll
+            for (u32 j = 0; j < 16; ++j) {
+                const u32 mixed = kmer_mix_x<R0>(__funnelshift_l(w1, w0, 2 * j), sh, mult, keymask, half);
+                const u32 tag = kmer_tag_of(mixed, pw + j);
+                const u32 v = table[mixed & (KMER_TAG_SLOTS - 1)];
+                mine += (v == tag) ? 1u : 0u;
+                if (((v ^ tag) >> KMER_TAG_IDX_BITS) == 0) m &= ~(1u << j); // representative or its duplicate
+            }
+        } else {
+#pragma unroll 4
+            for (u32 j = 0; j < 16; ++j) {
+                if ((m >> j) & 1u) {
+                    const u32 mixed = kmer_mix_x<R0>(__funnelshift_l(w1, w0, 2 * j), sh, mult, keymask, half);
+                    const u32 tag = kmer_tag_of(mixed, pw + j);
+                    const u32 v = table[mixed & (KMER_TAG_SLOTS - 1)];
+                    mine += (v == tag) ? 1u : 0u;
+                    if (((v ^ tag) >> KMER_TAG_IDX_BITS) == 0) m &= ~(1u << j);
+                }
+            }
+        }
+        pend[w] = (uint16_t)m;
+        left += __popc(m);
+    }
+    return mine;
+}
+
+// s_cnt: two u32 counters in shared memory.  Dense rounds walk the per-word masks; as soon as the pending
+// k-mers fit list_a (cap_a entries) they are compacted into a position list and the remaining rounds only
+// touch those (a round over the masks costs the same issue slots however few lanes are still pending).
+// The second list aliases pend[], which is dead once the first list is built.
+static __device__ u32 kmer_tag_count(const u32 *tile, u32 *table, uint16_t *pend, u32 *list_a, u32 cap_a,
+                                     u32 *s_cnt, u32 shift, u32 p_end, int k) {
+    const u32 kbits = 2u * (u32)k, sh = 32u - kbits, keymask = (1u << kbits) - 1u, half = max(kbits >> 1, 1u);
+    const u32 n_scan = (p_end + 15) >> 4; // words holding the start of at least one k-mer
+    const u32 lane = threadIdx.x & 31u;
+    for (u32 w = threadIdx.x; w < n_scan; w += blockDim.x) {
+        const u32 pw = w << 4;
+        u32 m = 0xFFFFu;
+        if (pw < shift) m &= 0xFFFFu << (shift - pw);
+        if (pw + 16 > p_end) m &= 0xFFFFu >> (pw + 16 - p_end);
+        pend[w] = (uint16_t)m;
+    }
+    if (threadIdx.x == 0) s_cnt[1] = 0;
+    u32 mine = 0, round = 0, n_list = 0;
+    for (;; ++round) { // ---- dense rounds ----
+        const u32 mult = 0x9E3779B1u + 0x3C6EF372u * round; // odd for every round
+        __syncthreads(); // pend / tile ready; everyone is done with the table and with s_cnt[0]
+        if (threadIdx.x == 0) s_cnt[0] = 0;
+        if (round == 0) kmer_dense_store<true>(tile, table, pend, n_scan, sh, mult, keymask, half);
+        else kmer_dense_store<false>(tile, table, pend, n_scan, sh, mult, keymask, half);
+        __syncthreads();
+        u32 left = 0;
+        if (round == 0) mine += kmer_dense_read<true>(tile, table, pend, n_scan, sh, mult, keymask, half, left);
+        else mine += kmer_dense_read<false>(tile, table, pend, n_scan, sh, mult, keymask, half, left);
+        left = __reduce_add_sync(0xffffffffu, left);
+        if (lane == 0 && left) atomicAdd(&s_cnt[0], left);
+        __syncthreads();
+        const u32 total = s_cnt[0];
+        if (total == 0) return mine;
+        if (total <= cap_a) { // compact the pending positions into list_a
+            const u32 n_iter = (n_scan + blockDim.x - 1) / blockDim.x;
+            for (u32 it = 0; it < n_iter; ++it) {
+                const u32 w = it * blockDim.x + threadIdx.x;
+                u32 m = (w < n_scan) ? pend[w] : 0u;
+                const u32 c = __popc(m);
+                u32 incl = c;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const u32 t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if ((int)lane >= d) incl += t;
+                }
+                const u32 wtot = __shfl_sync(0xffffffffu, incl, 31);
+                u32 base = 0;
+                if (lane == 0 && wtot) base = atomicAdd(&s_cnt[1], wtot);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                u32 off = base + incl - c;
+                while (m) {
+                    const u32 j = (u32)__ffs((int)m) - 1u;
+                    m &= m - 1u;
+                    list_a[off++] = (w << 4) + j;
+                }
+            }
+            n_list = total;
+            break;
+        }
+    }
+    // ---- list rounds ----
+    u32 *cur = list_a, *nxt = (u32 *)pend;
+    u32 ci = 0;
+    __syncthreads(); // list_a complete; pend[] is dead from here on
+    while (n_list) {
+        ++round;
+        const u32 mult = 0x9E3779B1u + 0x3C6EF372u * round;
+        if (threadIdx.x == 0) s_cnt[ci] = 0;
+        for (u32 i = threadIdx.x; i < n_list; i += blockDim.x) {
+            const u32 pos = cur[i], w = pos >> 4;
+            const u32 mixed = kmer_mix(__funnelshift_l(tile[w + 1], tile[w], 2 * (pos & 15u)) >> sh, mult, keymask, half);
+            table[mixed & (KMER_TAG_SLOTS - 1)] = kmer_tag_of(mixed, pos);
+        }
+        __syncthreads();
+        const u32 n_iter = (n_list + blockDim.x - 1) / blockDim.x;
+        for (u32 it = 0; it < n_iter; ++it) {
+            const u32 i = it * blockDim.x + threadIdx.x;
+            bool lost = false;
+            u32 pos = 0;
+            if (i < n_list) {
+                pos = cur[i];
+                const u32 w = pos >> 4;
+                const u32 mixed = kmer_mix(__funnelshift_l(tile[w + 1], tile[w], 2 * (pos & 15u)) >> sh, mult, keymask, half);
+                const u32 tag = kmer_tag_of(mixed, pos);
+                const u32 v = table[mixed & (KMER_TAG_SLOTS - 1)];
+                mine += (v == tag) ? 1u : 0u;
+                lost = ((v ^ tag) >> KMER_TAG_IDX_BITS) != 0;
+            }
+            const u32 bal = __ballot_sync(0xffffffffu, lost);
+            if (bal) {
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(&s_cnt[ci], (u32)__popc(bal));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (lost) nxt[base + __popc(bal & ((1u << lane) - 1u))] = pos;
+            }
+        }
+        __syncthreads();
+        n_list = s_cnt[ci];
+        u32 *t = cur; cur = nxt; nxt = t;
+        ci ^= 1u;
+    }
+    return mine;
+}
+
 __global__ void __launch_bounds__(KMER_SB_THREADS, 1)
 k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pieces_ptr,
-            u64 *__restrict__ counters, const u32 *__restrict__ dev_status) {
+            u64 *__restrict__ counters, const u32 *__restrict__ dev_status, int force_bitmap) {
     if (*dev_status != DEV_STATUS_OK) return;
     extern __shared__ __align__(16) uint8_t kmem[];
     u32 *bm = (u32 *)kmem;
     u32 *tile = (u32 *)(kmem + KMER_SB_BITMAP_BYTES);
     __shared__ u32 s_distinct;
+    __shared__ u32 s_cnt[2];
     const int k = P.kmer;
     const u32 keyspace = 1u << (2 * k);                       // k <= 12
     const u32 passes = (keyspace + KMER_SB_BITS - 1) / KMER_SB_BITS;
@@ -206,6 +421,17 @@ k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__
             const u32 n_tiles = ((u32)total + tile_kmers - 1) / tile_kmers;
             if (threadIdx.x == 0) s_distinct = 0;
             u32 mine = 0;
+            if (n_tiles == 1 && !force_bitmap) { // the whole piece fits one staged tile: tag rounds, no atomics
+                const u64 abase = seq0 & ~15ull;
+                const u32 shift = (u32)(seq0 - abase);
+                __syncthreads(); // the previous piece is done with tile / table
+                kmer_stage_tile(B, n_total, abase, (shift + (u32)total + (u32)k - 1 + 15) / 16, tile);
+                // shared layout of this path: table 128 KB | pend masks 24 KB (later: second list) | first list 20 KB | tile
+                mine = kmer_tag_count(tile, bm, (uint16_t *)(kmem + KMER_TAG_SLOTS * 4),
+                                      (u32 *)(kmem + KMER_TAG_SLOTS * 4 + KMER_SB_TILE_WORDS * 2),
+                                      (KMER_SB_BITMAP_BYTES - KMER_TAG_SLOTS * 4 - KMER_SB_TILE_WORDS * 2) / 4, s_cnt, shift,
+                                      shift + (u32)total, k);
+            } else
             for (u32 pass = 0; pass < passes; ++pass) {
                 const u32 lo = pass * KMER_SB_BITS;
                 __syncthreads(); // previous pass / piece is done with the bitmap
@@ -217,25 +443,7 @@ k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__
                     const u32 shift = (u32)(first - abase);  // position of k-mer 0 in the staged stream
                     if (n_tiles > 1 || pass == 0) {
                         if (t > 0 || n_tiles > 1) __syncthreads(); // readers of the previous tile are done
-                        const u32 n_bases_staged = shift + cnt + (u32)k - 1;
-                        const u32 n_words = (n_bases_staged + 15) / 16;
-                        for (u32 w = threadIdx.x; w < n_words + 1; w += KMER_SB_THREADS) {
-                            u32 v = 0;
-                            if (w < n_words) {
-                                const u64 a = abase + 16ull * w;
-                                uint4 q;
-                                if (a + 16 <= n_total) {
-                                    q = __ldg((const uint4 *)(B.bases + a));
-                                } else { // last, partial group of the batch: bytes beyond the stream are not touched
-                                    __align__(16) uint8_t tmp[16];
-#pragma unroll
-                                    for (int j = 0; j < 16; ++j) tmp[j] = (a + j < n_total) ? B.bases[a + j] : (uint8_t)0;
-                                    q = *(uint4 *)tmp;
-                                }
-                                v = (pack_codes4(q.x) << 24) | (pack_codes4(q.y) << 16) | (pack_codes4(q.z) << 8) | pack_codes4(q.w);
-                            }
-                            tile[w] = v; // tile[n_words] = 0: the window of the last word reads one word past it
-                        }
+                        kmer_stage_tile(B, n_total, abase, (shift + cnt + (u32)k - 1 + 15) / 16, tile);
                     }
                     __syncthreads(); // bitmap cleared, tile staged
                     // each thread: 16 consecutive stream positions of one word.  x = the 32 stream bits from

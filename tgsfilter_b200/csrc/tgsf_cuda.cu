@@ -220,6 +220,7 @@ struct tgsf_ctx {
     u32 head = 0, tail = 0, outstanding = 0; // ring: submit at head, collect at tail
     u64 launches = 0;
     bool kmer_force_l2 = false; // TGSF_KMER_L2=1: keep k <= 12 on the global-memory bitmap kernel (A/B, tests)
+    bool kmer_force_bitmap = false; // TGSF_KMER_BITMAP=1: shared-memory bitmap passes also for single-tile pieces
     float last_kernel_ms = 0, last_total_ms = 0;
     float last_stage_ms[TGSF_N_STAGES] = {};
 };
@@ -570,7 +571,7 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
         if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2) {
             // shared-memory bitmap in key-range passes
             k_kmer_smem<<<c->sm_count, KMER_SB_THREADS, KMER_SB_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
-                                                                                 &H->tmp_cursor, C, &H->status);
+                                                                                 &H->tmp_cursor, C, &H->status, c->kmer_force_bitmap ? 1 : 0);
             c->launches++;
         } else if (P.min_repeat > 0 && P.kmer <= 13) {
             // bitmap path: one 4^k-bit map per CTA, zeroed once and kept clean by the kernel
@@ -735,6 +736,7 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
         cudaError_t e1 = cudaFuncSetAttribute(k_scan_tiles_dyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(k_scan_tiles_dyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
         c->kmer_force_l2 = getenv("TGSF_KMER_L2") != nullptr;
+        c->kmer_force_bitmap = getenv("TGSF_KMER_BITMAP") != nullptr;
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         if (e4 == cudaSuccess) e4 = cudaFuncSetAttribute(k_kmer_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SB_SMEM_BYTES);
