@@ -3,12 +3,29 @@ sys.path.insert(0, os.getcwd())
 from tgsfilter_b200 import synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
 ext = sys.argv[2] if len(sys.argv) > 2 else ".fq"   # ".fq.gz": per-record gzip members like the reference
+in_gz = len(sys.argv) > 3 and sys.argv[3] == "gzin"  # feed a gzip -6 compressed input (16 members)
 batch = synth.make_config(2, n, with_names=False)
 d = "/dev/shm/f2f"; os.makedirs(d, exist_ok=True)
 fq = os.path.join(d, "in.fq")
 with open(fq, "wb") as f: f.write(batch.to_fastq())
 n_bases = batch.n_bases
 del batch
+if in_gz:
+    import gzip
+    from concurrent.futures import ProcessPoolExecutor
+    raw = open(fq, "rb").read()
+    # cut at record starts ("\n@read" only occurs at a header in this synthetic file: qualities are < '@')
+    cuts = [0]
+    for k in range(1, 16):
+        cuts.append(raw.index(b"\n@read", k * len(raw) // 16) + 1)
+    cuts.append(len(raw))
+    with ProcessPoolExecutor(16) as ex:
+        parts = list(ex.map(gzip.compress, [raw[a:b] for a, b in zip(cuts[:-1], cuts[1:])], [6] * 16))
+    fq = fq + ".gz"
+    with open(fq, "wb") as f:
+        for p_ in parts:
+            f.write(p_)
+    del raw, parts
 print("bases", n_bases, "file MB", os.path.getsize(fq) / 1e6)
 for name, exe, extra in (("host_b200", "src/tgsfilter", []), ("reference", "oracle/_ref/tgsfilter", ["-t", str(min(32, (os.cpu_count() or 2) - 1))])):
     out = os.path.join(d, name + ext)

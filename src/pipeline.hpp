@@ -1,7 +1,9 @@
 // Host ingest pipeline of the tgsfilter host: a reader thread parses
-// FASTQ/FASTA (plain or gzip, through zlib) straight out of a large read buffer into variable-length
+// FASTQ/FASTA (plain or gzip) straight out of a large read buffer into variable-length
 // batches, the main thread feeds the GPUs, a writer thread formats and writes the records.  Replaces
 // the reference's 1 reader + N workers + 1 writer joined by 1 ms-sleep polling (T.cpp:1808-1916).
+//
+// gzip input is decoded by the host's own inflate (inflate.hpp).
 //
 // The parser follows FastxReader's record rules (T.cpp:685-760): 4-line FASTQ / 2-line FASTA, a
 // record starts at the next line beginning with '@' / '>', '\r' before '\n' is dropped, an empty or
@@ -24,6 +26,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include "inflate.hpp"
 
 namespace ingest {
 
@@ -68,7 +72,10 @@ public:
         unsigned char magic[2] = {0, 0};
         const bool gz = probe && fread(magic, 1, 2, probe) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
         if (probe) fclose(probe);
-        if (gz) {
+        if (gz && !getenv("TGSF_ZLIB_INFLATE")) {
+            gz_.reset(new fastgz::GzReader(path)); // own inflate (src/inflate.hpp); zlib kept for A/B runs
+            if (!gz_->ok()) gz_.reset();
+        } else if (gz) {
             f_ = gzopen(path.c_str(), "rb");
             if (f_) gzbuffer(f_, 1 << 20);
         } else {
@@ -80,7 +87,7 @@ public:
         if (f_) gzclose(f_);
         if (fd_ >= 0) close(fd_);
     }
-    bool ok() const { return f_ != nullptr || fd_ >= 0; }
+    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr; }
 
     struct Rec { const char *name, *seq, *qual; size_t name_len, seq_len, qual_len; };
 
@@ -165,13 +172,17 @@ private:
         if (len_ == buf_.size()) buf_.resize(buf_.size() * 2); // one record larger than the buffer
         while (len_ < buf_.size()) {
             const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
-            const long got = f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want) : (long)read(fd_, buf_.data() + len_, want);
+            const long got = gz_ ? (long)gz_->read(buf_.data() + len_, want)
+                           : f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want)
+                                : (long)read(fd_, buf_.data() + len_, want);
+            if (gz_ && got == 0 && gz_->failed()) std::cerr << "Error: " << gz_->error() << " (gzip input)" << std::endl;
             if (got <= 0) { eof_ = true; break; }
             len_ += (size_t)got;
             if (len_ >= buf_.size() / 2) break;
         }
     }
     gzFile f_ = nullptr;
+    std::unique_ptr<fastgz::GzReader> gz_;
     int fd_ = -1;
     bool fastq_, eof_ = false;
     std::vector<char> buf_;

@@ -11,7 +11,7 @@ static uint64_t fnv(uint64_t h, const void *p, size_t n) {
 struct Digest {
     uint64_t h = 1469598103934665603ull, n = 0, bases = 0;
     void add(const ingest::RawBatch &b) {
-        if (getenv("INGEST_ONLY")) { n += b.n(); bases += b.bases.size(); return; }
+        if (getenv("INGEST_ONLY") && !getenv("INGEST_HASH")) { n += b.n(); bases += b.bases.size(); return; }
         for (size_t i = 0; i < b.n(); ++i) {
             h = fnv(h, b.names[i].data(), b.names[i].size());
             h = fnv(h, "\n", 1);

@@ -621,3 +621,20 @@ def test_kmer_repeat_length_on_every_kernel_path(k, monkeypatch):
         monkeypatch.delenv("TGSF_KMER_BITMAP")
         monkeypatch.setenv("TGSF_KMER_L2", "1")
         _compare(params, batch)
+
+
+@pytest.mark.parametrize("cfg,args", [(2, ["-x", "ont"]), (5, ["-x", "hifi", "-k", "11", "-p", "40"])])
+def test_host_cli_two_gpus_equals_one(cfg, args, monkeypatch):
+    """--gpus 2: batches alternate between two contexts, counters merged by tgsf_allreduce; records (in
+    input order), INFO lines and the report must equal the single-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("TGSF_BATCH_MB", "1")  # many small batches, so both GPUs get work
+    batch = synth.make_config(cfg, 600, max_len=40000)
+    fq = batch.to_fastq()
+    rc1, out1, err1 = _run_host_cli(args, fq)
+    rc2, out2, err2 = _run_host_cli(args + ["--gpus", "2"], fq)
+    assert rc1 == 0 and rc2 == 0, (err1, err2)
+    assert out1 == out2 and len(out1) > 0
+    assert _info(err1) == _info(err2)

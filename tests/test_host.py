@@ -286,6 +286,18 @@ def test_parallel_chunk_parser_equals_serial_reader(tmp_path, fastq):
             r = subprocess.run([exe, path, str(fastq), str(chunk), str(thr)], capture_output=True, text=True)
             assert r.returncode == 0, (crlf, chunk, thr, r.stdout, r.stderr)
             assert r.stdout.split()[0] == "1500"
+    # gzip input (two members, different levels) through the host's own inflate and through zlib
+    if fastq:
+        import gzip
+        raw = open(path, "rb").read()
+        gz = str(tmp_path / "in.fq.gz")
+        open(gz, "wb").write(gzip.compress(raw[:len(raw) // 2], 6) + gzip.compress(raw[len(raw) // 2:], 1))
+        env = dict(os.environ, INGEST_ONLY="serial", INGEST_HASH="1")
+        want = subprocess.run([exe, path, "1", "50000", "1"], capture_output=True, text=True, env=env).stdout.split()[:3]
+        got = subprocess.run([exe, gz, "1", "50000", "1"], capture_output=True, text=True, env=env).stdout.split()[:3]
+        got_zlib = subprocess.run([exe, gz, "1", "50000", "1"], capture_output=True, text=True,
+                                  env=dict(env, TGSF_ZLIB_INFLATE="1")).stdout.split()[:3]
+        assert want == got == got_zlib and want[0] == "1500"
     # unterminated last line and an empty file
     tail = str(tmp_path / "tail.fq")
     open(tail, "wb").write(b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII")
@@ -293,3 +305,58 @@ def test_parallel_chunk_parser_equals_serial_reader(tmp_path, fastq):
     empty = str(tmp_path / "empty.fq")
     open(empty, "wb").close()
     assert subprocess.run([exe, empty, "1", "64", "2"], capture_output=True).returncode == 0
+
+
+def test_own_inflate_matches_zlib(tmp_path):
+    """src/inflate.hpp (gzip input of the C++ host) against zlib: stored, fixed and dynamic blocks, every
+    strategy, multi-member files with header fields and zero padding, chunk-boundary sizes, corrupt and
+    truncated streams (both decoders must reject them)."""
+    import gzip
+    import io
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "inflate_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "inflate_check.cpp"), "-lz", "-o", exe],
+                   check=True)
+    rng = np.random.default_rng(3)
+    fq = synth.make_config(2, 120, with_names=False).to_fastq()
+    datasets = {
+        "fastq": fq,
+        "random": rng.integers(0, 256, 1_500_000, dtype=np.uint8).tobytes(),
+        "runs": (b"A" * 100000 + b"CG" * 50000 + b"ACGTACG" * 30000 + bytes(rng.integers(65, 70, 1000, dtype=np.uint8))) * 6,
+        "text": b"the quick brown fox jumps over the lazy dog. " * 20000,
+        "empty": b"",
+        "one": b"x",
+    }
+
+    def comp(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31, 8, strategy)
+        return c.compress(data) + c.flush()
+
+    path = str(tmp_path / "t.gz")
+
+    def check(blob, what, read_sizes=("1048576",)):
+        with open(path, "wb") as f:
+            f.write(blob)
+        for rs in read_sizes:
+            r = subprocess.run([exe, path, rs], capture_output=True, text=True)
+            assert r.returncode == 0, (what, rs, r.stdout, r.stderr)
+
+    for name, d in datasets.items():
+        variants = [("l%d" % lv, comp(d, lv)) for lv in (0, 1, 6, 9)]
+        variants += [("fixed", comp(d, 6, zlib.Z_FIXED)), ("huff", comp(d, 6, zlib.Z_HUFFMAN_ONLY)),
+                     ("rle", comp(d, 6, zlib.Z_RLE))]
+        bio = io.BytesIO()
+        for part in (d[:len(d) // 3], d[len(d) // 3:2 * len(d) // 3], b"", d[2 * len(d) // 3:]):
+            with gzip.GzipFile(filename="some_name.fq", mode="wb", fileobj=bio, compresslevel=5) as g:
+                g.write(part)
+        variants.append(("multi", bio.getvalue() + b"\0\0\0\0"))
+        for vn, z in variants:
+            check(z, (name, vn), ("1048576",) if len(d) > 100000 else ("7", "1048576"))
+    z = bytearray(comp(fq[:200000], 6))
+    for pos in (50, 1000, len(z) // 2, len(z) - 5, len(z) - 9):
+        zz = bytearray(z)
+        zz[pos] ^= 0x55
+        check(bytes(zz), ("corrupt", pos))
+    check(bytes(z[:len(z) // 2]), "truncated")
