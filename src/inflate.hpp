@@ -15,9 +15,14 @@
 #include <unistd.h>
 #include <zlib.h> // crc32() only
 
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace fastgz {
@@ -97,10 +102,12 @@ inline bool build_table(const uint8_t *lens, int n, int primary, Entry *table, i
 // Multi-literal view of a literal/length primary table: entry i packs up to three literals that are fully
 // determined by the LIT_BITS index bits (FASTQ bases have 2-3 bit codes, so one lookup yields 2-3 bytes).
 // bit 31: valid pack, bits 28-29: count, bits 24-27: bits to consume, bits 0-23: the literals, first one lowest.
+// Other entries carry the Entry itself (val | nbits << 16 | op << 24; op 0x80 moved to bit 30), so the
+// length / end-of-block / link dispatch needs no second load.
 inline void build_multi_literal(const Entry *lit, uint32_t *multi) {
     for (unsigned i = 0; i < (1u << LIT_BITS); ++i) {
         const Entry e1 = lit[i];
-        if (e1.op != 0) { multi[i] = 0; continue; }
+        if (e1.op != 0) { multi[i] = (uint32_t)e1.val | ((uint32_t)e1.nbits << 16) | ((uint32_t)(e1.op & 0x7F) << 24) | ((e1.op & 0x80) ? (1u << 30) : 0u); continue; }
         unsigned n = e1.nbits, cnt = 1;
         uint32_t bytes = e1.val;
         const Entry e2 = lit[i >> n];
@@ -136,8 +143,24 @@ public:
         }
         init_memory();
     }
-    // decode from a memory range (tests)
+    // decode from a memory range (tests, BGZF block groups)
     GzReader(const uint8_t *data, size_t n) : base_(data), size_(n), borrowed_(true) { init_memory(); }
+    // point the decoder at another memory range (keeps the buffers)
+    void reset(const uint8_t *data, size_t n) {
+        base_ = data;
+        size_ = n;
+        borrowed_ = true;
+        done_ = in_member_ = last_block_ = false;
+        error_ = nullptr;
+        bitbuf_ = 0;
+        bitcnt_ = overrun_ = 0;
+        member_out_ = 0;
+        state_ = BLOCK_HEADER;
+        out_ = rd_ = wr_ = crc_from_ = buf_.data() + HIST;
+        in_ = base_;
+        end_ = base_ + size_;
+        if (size_ == 0) done_ = true;
+    }
     ~GzReader() {
         if (base_ && !borrowed_) munmap((void *)base_, size_);
         if (fd_ >= 0) close(fd_);
@@ -166,7 +189,7 @@ public:
 
 private:
     void init_memory() {
-        buf_.resize(HIST + CHUNK + SLACK + 8);
+        if (buf_.empty()) buf_.resize(HIST + CHUNK + SLACK + 8);
         out_ = rd_ = wr_ = buf_.data() + HIST;
         in_ = base_;
         end_ = base_ + size_;
@@ -443,8 +466,16 @@ private:
                 }
 #undef FGZ_EMIT
                 FGZ_REFILL(); // a length/distance pair may need 48 bits
+                m = multi[bb & ((1u << LIT_BITS) - 1)];
             }
-            Entry e = lit[bb & ((1u << LIT_BITS) - 1)];
+            Entry e;
+            if (m >> 31) { // (only after the refill above) a literal again: take the plain entry
+                e = lit[bb & ((1u << LIT_BITS) - 1)];
+            } else {
+                e.val = (uint16_t)m;
+                e.nbits = (uint8_t)(m >> 16);
+                e.op = (uint8_t)(((m >> 24) & 0x7F) | ((m >> 30) & 1u ? 0x80 : 0));
+            }
             if (e.op & 0x20) { // second-level table
                 bb >>= e.nbits; bc -= e.nbits;
                 e = lit[e.val + (bb & ((1u << (e.op & 15)) - 1))];
@@ -505,6 +536,172 @@ private:
     State state_ = BLOCK_HEADER;
     Entry lit_[LIT_TABLE], dist_[DIST_TABLE];
     uint32_t multi_[1 << LIT_BITS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// BGZF (bgzip, samtools fastq, htslib): every member is a <= 64 KB block whose header carries its own
+// compressed size ("BC" extra subfield), so the member boundaries are known without decoding.  The
+// file is cut into groups of consecutive blocks (~8 MB compressed, each group is itself a valid
+// multi-member gzip stream); worker threads decode groups independently, read() serves them in file
+// order.  Data after the last BGZF block (a plain gzip member appended to the file) is decoded by a
+// streaming GzReader once the groups are consumed.
+// ---------------------------------------------------------------------------------------------
+class BgzfParallelReader {
+public:
+    // BSIZE + 1 of the block at p, or 0 when p is not a BGZF block header
+    static size_t block_size(const uint8_t *p, size_t n) {
+        if (n < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || !(p[3] & 4)) return 0;
+        const size_t xlen = p[10] | (p[11] << 8);
+        if (n < 12 + xlen) return 0;
+        for (size_t q = 12; q + 4 <= 12 + xlen;) {
+            const size_t slen = p[q + 2] | (p[q + 3] << 8);
+            if (p[q] == 'B' && p[q + 1] == 'C' && slen == 2 && q + 6 <= 12 + xlen) return (size_t)(p[q + 4] | (p[q + 5] << 8)) + 1;
+            q += 4 + slen;
+        }
+        return 0;
+    }
+    static bool is_bgzf(const std::string &path) {
+        uint8_t h[64];
+        FILE *f = fopen(path.c_str(), "rb");
+        const size_t n = f ? fread(h, 1, sizeof(h), f) : 0;
+        if (f) fclose(f);
+        return block_size(h, n) != 0;
+    }
+
+    BgzfParallelReader(const std::string &path, int threads) {
+        fd_ = open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd_ < 0 || fstat(fd_, &st) != 0) return;
+        size_ = (size_t)st.st_size;
+        if (size_) {
+            void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m == MAP_FAILED) return;
+            base_ = (const uint8_t *)m;
+        }
+        ok_ = true;
+        window_ = (size_t)std::max(4, 2 * threads);
+        for (int t = 0; t < std::max(1, threads); ++t) workers_.emplace_back([this] { work(); });
+    }
+    ~BgzfParallelReader() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+        if (base_) munmap((void *)base_, size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    bool ok() const { return ok_; }
+    bool failed() const { return error_ != nullptr; }
+    const char *error() const { return error_; }
+
+    size_t read(void *dst, size_t n) {
+        uint8_t *d = (uint8_t *)dst;
+        size_t got = 0;
+        while (got < n && !error_) {
+            if (tail_) { // streaming remainder
+                const size_t k = tail_->read(d + got, n - got);
+                if (k == 0) { if (tail_->failed()) error_ = tail_->error(); break; }
+                got += k;
+                continue;
+            }
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return !tasks_.empty() ? tasks_.front()->state == 2 : scan_done_; });
+            if (tasks_.empty()) { // all groups consumed
+                lk.unlock();
+                if (scan_off_ < size_) { tail_.reset(new GzReader(base_ + scan_off_, size_ - scan_off_)); continue; }
+                break;
+            }
+            Task &t = *tasks_.front();
+            if (t.err) { error_ = t.err; break; }
+            lk.unlock();
+            const size_t k = std::min(n - got, t.out.size() - t.pos);
+            memcpy(d + got, t.out.data() + t.pos, k);
+            t.pos += k;
+            got += k;
+            if (t.pos == t.out.size()) {
+                lk.lock();
+                tasks_.pop_front();
+                lk.unlock();
+                cv_.notify_all();
+            }
+        }
+        return got;
+    }
+
+private:
+    struct Task {
+        size_t a = 0, b = 0, pos = 0;
+        std::vector<uint8_t> out;
+        int state = 0; // 1 decoding, 2 ready
+        const char *err = nullptr;
+    };
+    // next group of blocks from scan_off_ (m_ held); nullptr when the BGZF part is exhausted
+    Task *next_task() {
+        if (scan_done_) return nullptr;
+        size_t a = scan_off_, b = a, out = 0;
+        while (b < size_ && b - a < (8u << 20)) {
+            const size_t bs = block_size(base_ + b, size_ - b);
+            if (bs < 26 || b + bs > size_) break; // not a (complete) BGZF block: the remainder is streamed
+            uint32_t isize;
+            memcpy(&isize, base_ + b + bs - 4, 4);
+            out += isize;
+            b += bs;
+        }
+        if (b == a) { scan_done_ = true; return nullptr; }
+        scan_off_ = b;
+        if (b >= size_) scan_done_ = true;
+        tasks_.emplace_back(new Task());
+        Task *t = tasks_.back().get();
+        t->a = a;
+        t->b = b;
+        t->out.resize(out);
+        t->state = 1;
+        return t;
+    }
+    void work() {
+        GzReader rd(nullptr, 0);
+        while (true) {
+            Task *t;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || scan_done_ || tasks_.size() < window_; });
+                if (stop_) return;
+                t = next_task();
+                if (!t) { cv_.notify_all(); return; }
+            }
+            rd.reset(base_ + t->a, t->b - t->a);
+            size_t got = 0;
+            while (got < t->out.size()) {
+                const size_t k = rd.read(t->out.data() + got, t->out.size() - got);
+                if (k == 0) break;
+                got += k;
+            }
+            uint8_t extra;
+            const char *err = nullptr;
+            if (rd.failed()) err = rd.error();
+            else if (got != t->out.size() || rd.read(&extra, 1) != 0) err = "BGZF block length mismatch";
+            else if (rd.failed()) err = rd.error(); // CRC of the last block is checked when its end is reached
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                t->err = err;
+                t->state = 2;
+            }
+            cv_.notify_all();
+        }
+    }
+
+    int fd_ = -1;
+    const uint8_t *base_ = nullptr;
+    size_t size_ = 0, scan_off_ = 0, window_ = 8;
+    bool ok_ = false, stop_ = false, scan_done_ = false;
+    const char *error_ = nullptr;
+    std::deque<std::unique_ptr<Task>> tasks_;
+    std::vector<std::thread> workers_;
+    std::unique_ptr<GzReader> tail_;
+    std::mutex m_;
+    std::condition_variable cv_;
 };
 
 }  // namespace fastgz

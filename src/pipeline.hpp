@@ -72,9 +72,29 @@ public:
         unsigned char magic[2] = {0, 0};
         const bool gz = probe && fread(magic, 1, 2, probe) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
         if (probe) fclose(probe);
-        if (gz && !getenv("TGSF_ZLIB_INFLATE")) {
+        if (gz && !getenv("TGSF_ZLIB_INFLATE") && inflate_threads() > 1 && fastgz::BgzfParallelReader::is_bgzf(path)) {
+            bgzf_.reset(new fastgz::BgzfParallelReader(path, inflate_threads())); // block groups decoded in parallel
+            if (!bgzf_->ok()) bgzf_.reset();
+        } else if (gz && !getenv("TGSF_ZLIB_INFLATE")) {
             gz_.reset(new fastgz::GzReader(path)); // own inflate (src/inflate.hpp); zlib kept for A/B runs
             if (!gz_->ok()) gz_.reset();
+            else inflater_ = std::thread([this] { // decode ahead of the parser, 4 MB chunks
+                while (true) {
+                    std::unique_ptr<std::vector<char>> c;
+                    {
+                        std::lock_guard<std::mutex> lk(spare_m_);
+                        if (!spare_.empty()) { c = std::move(spare_.back()); spare_.pop_back(); }
+                    }
+                    if (!c) c.reset(new std::vector<char>(4u << 20));
+                    c->resize(4u << 20);
+                    const size_t n = gz_->read(c->data(), c->size());
+                    if (n == 0) break;
+                    c->resize(n);
+                    chunks_.push(std::move(c));
+                    if (stop_inflater_.load()) break;
+                }
+                chunks_.push(nullptr);
+            });
         } else if (gz) {
             f_ = gzopen(path.c_str(), "rb");
             if (f_) gzbuffer(f_, 1 << 20);
@@ -84,10 +104,19 @@ public:
         buf_.resize(8u << 20);
     }
     ~FastParser() {
+        if (inflater_.joinable()) {
+            stop_inflater_.store(true);
+            while (!chunks_done_) { if (!chunks_.pop()) chunks_done_ = true; } // unblock and drain
+            inflater_.join();
+        }
         if (f_) gzclose(f_);
         if (fd_ >= 0) close(fd_);
     }
-    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr; }
+    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr || bgzf_ != nullptr; }
+    static int inflate_threads() { // TGSF_INFLATE_THREADS, default min(8, cores - 2)
+        if (const char *e = getenv("TGSF_INFLATE_THREADS")) return std::max(1, atoi(e));
+        return std::max(1, std::min(8, (int)std::thread::hardware_concurrency() - 2));
+    }
 
     struct Rec { const char *name, *seq, *qual; size_t name_len, seq_len, qual_len; };
 
@@ -172,17 +201,48 @@ private:
         if (len_ == buf_.size()) buf_.resize(buf_.size() * 2); // one record larger than the buffer
         while (len_ < buf_.size()) {
             const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
-            const long got = gz_ ? (long)gz_->read(buf_.data() + len_, want)
+            const long got = bgzf_ ? (long)bgzf_->read(buf_.data() + len_, want)
+                           : gz_ ? (long)read_inflated(buf_.data() + len_, want)
                            : f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want)
                                 : (long)read(fd_, buf_.data() + len_, want);
+            if (bgzf_ && got == 0 && bgzf_->failed()) std::cerr << "Error: " << bgzf_->error() << " (BGZF input)" << std::endl;
             if (gz_ && got == 0 && gz_->failed()) std::cerr << "Error: " << gz_->error() << " (gzip input)" << std::endl;
             if (got <= 0) { eof_ = true; break; }
             len_ += (size_t)got;
             if (len_ >= buf_.size() / 2) break;
         }
     }
+    size_t read_inflated(char *dst, size_t want) { // bytes of the decoder thread's chunks, in order
+        size_t got = 0;
+        while (got < want && !chunks_done_) {
+            if (!cur_ || cur_pos_ == cur_->size()) {
+                if (cur_) {
+                    std::lock_guard<std::mutex> lk(spare_m_);
+                    if (spare_.size() < 4) spare_.push_back(std::move(cur_));
+                }
+                cur_ = chunks_.pop();
+                cur_pos_ = 0;
+                if (!cur_) { chunks_done_ = true; break; }
+            }
+            const size_t n = std::min(want - got, cur_->size() - cur_pos_);
+            memcpy(dst + got, cur_->data() + cur_pos_, n);
+            cur_pos_ += n;
+            got += n;
+            if (got) break; // hand over what is there; the caller asks again
+        }
+        return got;
+    }
     gzFile f_ = nullptr;
     std::unique_ptr<fastgz::GzReader> gz_;
+    std::unique_ptr<fastgz::BgzfParallelReader> bgzf_;
+    std::thread inflater_;
+    std::atomic<bool> stop_inflater_{false};
+    Queue<std::unique_ptr<std::vector<char>>> chunks_{4};
+    std::unique_ptr<std::vector<char>> cur_;
+    size_t cur_pos_ = 0;
+    bool chunks_done_ = false;
+    std::mutex spare_m_;
+    std::vector<std::unique_ptr<std::vector<char>>> spare_;
     int fd_ = -1;
     bool fastq_, eof_ = false;
     std::vector<char> buf_;

@@ -298,6 +298,34 @@ def test_parallel_chunk_parser_equals_serial_reader(tmp_path, fastq):
         got_zlib = subprocess.run([exe, gz, "1", "50000", "1"], capture_output=True, text=True,
                                   env=dict(env, TGSF_ZLIB_INFLATE="1")).stdout.split()[:3]
         assert want == got == got_zlib and want[0] == "1500"
+        # BGZF (block sizes in the headers: groups of blocks are decoded in parallel), BGZF followed by a
+        # plain gzip member, and a corrupted block
+        import struct
+        import zlib
+
+        def bgzf(data, blk=65280):
+            out = bytearray()
+            for i in list(range(0, len(data), blk)) + [None]:
+                chunk = b"" if i is None else data[i:i + blk]
+                c = zlib.compressobj(6, zlib.DEFLATED, -15)
+                d = c.compress(chunk) + c.flush()
+                out += (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(d) + 25) + d +
+                        struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+            return bytes(out)
+
+        env4 = dict(env, TGSF_INFLATE_THREADS="4")
+        z = bgzf(raw)
+        assert gzip.decompress(z) == raw
+        for name, blob in (("bgzf", z), ("mixed", bgzf(raw[:len(raw) // 2]) + gzip.compress(raw[len(raw) // 2:]))):
+            pth = str(tmp_path / (name + ".fq.gz"))
+            open(pth, "wb").write(blob)
+            assert subprocess.run([exe, pth, "1", "50000", "1"], capture_output=True, text=True, env=env4).stdout.split()[:3] == want
+        bad = bytearray(z)
+        bad[len(bad) // 2] ^= 0x10
+        pth = str(tmp_path / "bad.fq.gz")
+        open(pth, "wb").write(bytes(bad))
+        r = subprocess.run([exe, pth, "1", "50000", "1"], capture_output=True, text=True, env=env4)
+        assert "BGZF input" in r.stderr and int(r.stdout.split()[0]) < 1500
     # unterminated last line and an empty file
     tail = str(tmp_path / "tail.fq")
     open(tail, "wb").write(b"@a\nACGT\n+\nIIII\n@b\nAC\n+\nII")
