@@ -10,6 +10,7 @@ TIMEFORMAT="%R s"
 t() { time "$@" > /dev/null; }
 echo -n "plain, parallel chunk parser (8 thr): "; INGEST_ONLY=parallel t /tmp/ingest_check /dev/shm/f2f/in.fq 1 134217728 8
 echo -n "plain, serial reader:                 "; INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in.fq 1 67108864 1
-echo -n "gzip 16 members, own inflate:         "; INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in16.fq.gz 1 67108864 1
+echo -n "gzip 16 members, own inflate, 1 thr:  "; TGSF_INFLATE_THREADS=1 INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in16.fq.gz 1 67108864 1
 echo -n "gzip 16 members, zlib:                "; TGSF_ZLIB_INFLATE=1 INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in16.fq.gz 1 67108864 1
+for n in 1 2 4 8; do echo -n "gzip 16 members, $n inflate threads:   "; TGSF_INFLATE_THREADS=$n INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in16.fq.gz 1 67108864 1; done
 for n in 1 2 4 8; do echo -n "BGZF, $n inflate threads:              "; TGSF_INFLATE_THREADS=$n INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in.fq.gz 1 67108864 1; done

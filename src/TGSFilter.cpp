@@ -511,6 +511,11 @@ int main(int argc, char **argv) {
     const bool stream_input = P.Filter || P.OnlyQC;
     if (stream_input) {
         { gzFile probe = gzopen(P.InFile.c_str(), "rb"); if (!probe) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; } gzclose(probe); }
+        // CUDA context creation (0.4-0.7 s warm, 1.3 s+ for the first process on a box) overlaps the parsing;
+        // TGSF_INIT_FIRST=1 creates it before the parser threads start (measured: no faster)
+        const bool init_first = getenv("TGSF_INIT_FIRST") != nullptr;
+        auto warm_up = [&]() { Timer tw; void *warm = nullptr; if (tgsf_host_alloc(&warm, 1 << 20) == TGSF_OK) tgsf_host_free(warm); tlog("  CUDA context warm-up", tw.lap()); };
+        if (init_first) warm_up();
         if (!ingest::ParallelReader::is_gzip(P.InFile) && !getenv("TGSF_SERIAL_READER")) {
             const int hw = (int)std::thread::hardware_concurrency();
             const int nthr = getenv("TGSF_PARSE_THREADS") ? atoi(getenv("TGSF_PARSE_THREADS")) : std::max(1, std::min(8, hw - 2));
@@ -519,7 +524,7 @@ int main(int argc, char **argv) {
         } else {
             reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool);
         }
-        { Timer tw; void *warm = nullptr; if (tgsf_host_alloc(&warm, 1 << 20) == TGSF_OK) tgsf_host_free(warm); tlog("  CUDA context warm-up", tw.lap()); } // CUDA context up while the reader parses
+        if (!init_first) warm_up();
         while (!input_done && seqNum < maxSeq) {
             std::unique_ptr<ingest::RawBatch> rb = next_parsed();
             if (!rb) { input_done = true; break; }
@@ -779,7 +784,7 @@ int main(int argc, char **argv) {
                 if (!obuf.empty()) { fwrite(obuf.data(), 1, obuf.size(), out); obuf.clear(); }
             } else if (!emits.empty()) {
                 // split the records into contiguous ranges of about equal payload
-                const int K = gz_now ? out_threads : (out_regular ? std::min(out_threads, 4) : 1);
+                const int K = gz_now ? out_threads : (out_regular ? std::min(out_threads, 8) : 1);
                 std::vector<size_t> cut((size_t)K + 1, emits.size());
                 std::vector<uint64_t> bytes_before((size_t)K + 1, 0);
                 {

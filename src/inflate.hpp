@@ -155,6 +155,7 @@ public:
         bitbuf_ = 0;
         bitcnt_ = overrun_ = 0;
         member_out_ = 0;
+        stop_ = (size_t)-1;
         state_ = BLOCK_HEADER;
         out_ = rd_ = wr_ = crc_from_ = buf_.data() + HIST;
         in_ = base_;
@@ -168,6 +169,10 @@ public:
     bool ok() const { return ok_; }
     bool failed() const { return error_ != nullptr; }
     const char *error() const { return error_; }
+    // stop at the first member boundary at or beyond this input offset (default: end of input)
+    void set_stop(size_t off) { stop_ = off; }
+    // input bytes consumed up to the last finished member (valid once read() has returned 0 without error)
+    size_t consumed() const { return (size_t)(in_ - base_); }
 
     // Up to n decoded bytes into dst; 0 at the end of the stream or after an error (see failed()).
     size_t read(void *dst, size_t n) {
@@ -273,6 +278,7 @@ private:
         if (crc != crc_) { fail("gzip CRC mismatch"); return false; }
         if (isize != (uint32_t)member_out_) { fail("gzip length mismatch"); return false; }
         in_member_ = false;
+        if ((size_t)(in_ - base_) >= stop_) done_ = true; // member boundary at or beyond the requested stop
         return true;
     }
     void flush_crc() { // bytes [crc_from_, out_) belong to the current member and are not summed yet
@@ -523,7 +529,7 @@ private:
 
     int fd_ = -1;
     const uint8_t *base_ = nullptr;
-    size_t size_ = 0;
+    size_t size_ = 0, stop_ = (size_t)-1;
     bool borrowed_ = false, ok_ = false, done_ = false, in_member_ = false, last_block_ = false;
     const char *error_ = nullptr;
     std::vector<uint8_t> buf_;
@@ -695,6 +701,205 @@ private:
     int fd_ = -1;
     const uint8_t *base_ = nullptr;
     size_t size_ = 0, scan_off_ = 0, window_ = 8;
+    bool ok_ = false, stop_ = false, scan_done_ = false;
+    const char *error_ = nullptr;
+    std::deque<std::unique_ptr<Task>> tasks_;
+    std::vector<std::thread> workers_;
+    std::unique_ptr<GzReader> tail_;
+    std::mutex m_;
+    std::condition_variable cv_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Concatenated gzip members without block-size headers (`cat *.fastq.gz` of a sequencing run, this
+// tool's own per-record members): member starts are *guessed* by scanning for a plausible gzip header,
+// spans of ~8 MB between guesses are decoded speculatively in parallel, and the consumer accepts a
+// span only if it starts exactly where the previous accepted span ended (span 0 starts at offset 0).
+// A decoder started at a true member start stops only at member boundaries, so an accepted chain is
+// exactly the sequential decode.  Any anomaly — a guess inside compressed data, a span that fails or
+// grows beyond the memory cap — switches to the streaming decoder from the last verified boundary,
+// which reproduces the sequential behaviour (including its error, after the good prefix).
+// ---------------------------------------------------------------------------------------------
+class MultiMemberReader {
+public:
+    enum : size_t { SPAN = 8u << 20, SPAN_OUT_CAP = 1u << 30 };
+
+    // offset of the first plausible member header at or after `from`, or n
+    static size_t next_candidate(const uint8_t *p, size_t n, size_t from) {
+        while (from + 18 <= n) {
+            const uint8_t *q = (const uint8_t *)memchr(p + from, 0x1f, n - from - 17);
+            if (!q) return n;
+            const size_t o = (size_t)(q - p);
+            if (q[1] == 0x8b && q[2] == 8 && (q[3] & 0xE0) == 0 && (q[8] == 0 || q[8] == 2 || q[8] == 4) && (q[9] <= 13 || q[9] == 255))
+                return o;
+            from = o + 1;
+        }
+        return n;
+    }
+    // worth going parallel: a second member header within the first 64 MB
+    static bool is_multi_member(const std::string &path) {
+        const int fd = open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        std::vector<uint8_t> head(1u << 20);
+        bool found = false;
+        size_t off = 0;
+        uint8_t carry[17];
+        size_t ncarry = 0;
+        while (!found && off < (64u << 20)) {
+            memcpy(head.data(), carry, ncarry);
+            const ssize_t got = ::read(fd, head.data() + ncarry, head.size() - ncarry);
+            if (got <= 0) break;
+            const size_t n = ncarry + (size_t)got;
+            const size_t c = next_candidate(head.data(), n, off == 0 ? 1 : 0);
+            if (c < n) found = true;
+            ncarry = std::min<size_t>(17, n);
+            memcpy(carry, head.data() + n - ncarry, ncarry);
+            off += (size_t)got;
+        }
+        close(fd);
+        return found;
+    }
+
+    MultiMemberReader(const std::string &path, int threads) {
+        fd_ = open(path.c_str(), O_RDONLY);
+        struct stat st;
+        if (fd_ < 0 || fstat(fd_, &st) != 0) return;
+        size_ = (size_t)st.st_size;
+        if (size_) {
+            void *m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m == MAP_FAILED) return;
+            base_ = (const uint8_t *)m;
+        }
+        ok_ = true;
+        window_ = (size_t)std::max(4, 2 * threads);
+        for (int t = 0; t < std::max(1, threads); ++t) workers_.emplace_back([this] { work(); });
+    }
+    ~MultiMemberReader() {
+        shutdown();
+        if (base_) munmap((void *)base_, size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    bool ok() const { return ok_; }
+    bool failed() const { return error_ != nullptr; }
+    const char *error() const { return error_; }
+    bool fell_back() const { return tail_ != nullptr; } // tests
+
+    size_t read(void *dst, size_t n) {
+        uint8_t *d = (uint8_t *)dst;
+        size_t got = 0;
+        while (got < n && !error_) {
+            if (tail_) {
+                const size_t k = tail_->read(d + got, n - got);
+                if (k == 0) { if (tail_->failed()) error_ = tail_->error(); break; }
+                got += k;
+                continue;
+            }
+            std::unique_lock<std::mutex> lk(m_);
+            cv_.wait(lk, [&] { return !tasks_.empty() ? tasks_.front()->state == 2 : scan_done_; });
+            if (tasks_.empty()) {
+                lk.unlock();
+                if (expected_ < size_) fallback(); // bytes after the last span (cannot happen for well-formed input)
+                else break;
+                continue;
+            }
+            Task &t = *tasks_.front();
+            lk.unlock();
+            if (t.pos == 0 && (t.start != expected_ || t.err || t.too_big)) { fallback(); continue; }
+            const size_t k = std::min(n - got, t.out.size() - t.pos);
+            memcpy(d + got, t.out.data() + t.pos, k);
+            t.pos += k;
+            got += k;
+            if (t.pos == t.out.size()) {
+                expected_ = t.end;
+                lk.lock();
+                tasks_.pop_front();
+                lk.unlock();
+                cv_.notify_all();
+            }
+        }
+        return got;
+    }
+
+private:
+    struct Task {
+        size_t start = 0, stop = 0, end = 0, pos = 0;
+        std::vector<uint8_t> out;
+        int state = 0;
+        const char *err = nullptr;
+        bool too_big = false;
+    };
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &w : workers_) w.join();
+        workers_.clear();
+    }
+    void fallback() { // sequential decode from the last verified member boundary
+        shutdown();
+        tasks_.clear();
+        tail_.reset(new GzReader(base_ + expected_, size_ - expected_));
+    }
+    Task *next_task() { // m_ held
+        if (scan_done_) return nullptr;
+        const size_t start = scan_off_;
+        if (start >= size_) { scan_done_ = true; return nullptr; }
+        const size_t stop = start + SPAN >= size_ ? size_ : next_candidate(base_, size_, start + SPAN);
+        scan_off_ = stop;
+        if (stop >= size_) scan_done_ = true;
+        tasks_.emplace_back(new Task());
+        Task *t = tasks_.back().get();
+        t->start = start;
+        t->stop = stop;
+        t->state = 1;
+        return t;
+    }
+    void work() {
+        GzReader rd(nullptr, 0);
+        while (true) {
+            Task *t;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || scan_done_ || tasks_.size() < window_; });
+                if (stop_) return;
+                t = next_task();
+                if (!t) { cv_.notify_all(); return; }
+            }
+            rd.reset(base_ + t->start, size_ - t->start);
+            rd.set_stop(t->stop - t->start);
+            t->out.resize(std::min<size_t>(4 * (t->stop - t->start) + (1u << 20), 64u << 20));
+            size_t got = 0;
+            while (true) {
+                if (got == t->out.size()) {
+                    if (got >= SPAN_OUT_CAP) { t->too_big = true; break; }
+                    t->out.resize(got * 2);
+                }
+                const size_t k = rd.read(t->out.data() + got, t->out.size() - got);
+                if (k == 0) break;
+                got += k;
+                if (stop_flag()) break;
+            }
+            t->out.resize(got);
+            const char *err = rd.failed() ? rd.error() : nullptr;
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                t->err = err;
+                t->end = t->start + rd.consumed();
+                t->state = 2;
+            }
+            cv_.notify_all();
+        }
+    }
+    bool stop_flag() {
+        std::lock_guard<std::mutex> lk(m_);
+        return stop_;
+    }
+
+    int fd_ = -1;
+    const uint8_t *base_ = nullptr;
+    size_t size_ = 0, scan_off_ = 0, expected_ = 0, window_ = 8;
     bool ok_ = false, stop_ = false, scan_done_ = false;
     const char *error_ = nullptr;
     std::deque<std::unique_ptr<Task>> tasks_;

@@ -75,6 +75,9 @@ public:
         if (gz && !getenv("TGSF_ZLIB_INFLATE") && inflate_threads() > 1 && fastgz::BgzfParallelReader::is_bgzf(path)) {
             bgzf_.reset(new fastgz::BgzfParallelReader(path, inflate_threads())); // block groups decoded in parallel
             if (!bgzf_->ok()) bgzf_.reset();
+        } else if (gz && !getenv("TGSF_ZLIB_INFLATE") && inflate_threads() > 1 && fastgz::MultiMemberReader::is_multi_member(path)) {
+            mm_.reset(new fastgz::MultiMemberReader(path, inflate_threads())); // concatenated members, speculative spans
+            if (!mm_->ok()) mm_.reset();
         } else if (gz && !getenv("TGSF_ZLIB_INFLATE")) {
             gz_.reset(new fastgz::GzReader(path)); // own inflate (src/inflate.hpp); zlib kept for A/B runs
             if (!gz_->ok()) gz_.reset();
@@ -112,7 +115,7 @@ public:
         if (f_) gzclose(f_);
         if (fd_ >= 0) close(fd_);
     }
-    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr || bgzf_ != nullptr; }
+    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr || bgzf_ != nullptr || mm_ != nullptr; }
     static int inflate_threads() { // TGSF_INFLATE_THREADS, default min(8, cores - 2)
         if (const char *e = getenv("TGSF_INFLATE_THREADS")) return std::max(1, atoi(e));
         return std::max(1, std::min(8, (int)std::thread::hardware_concurrency() - 2));
@@ -201,10 +204,12 @@ private:
         if (len_ == buf_.size()) buf_.resize(buf_.size() * 2); // one record larger than the buffer
         while (len_ < buf_.size()) {
             const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
-            const long got = bgzf_ ? (long)bgzf_->read(buf_.data() + len_, want)
+            const long got = mm_ ? (long)mm_->read(buf_.data() + len_, want)
+                           : bgzf_ ? (long)bgzf_->read(buf_.data() + len_, want)
                            : gz_ ? (long)read_inflated(buf_.data() + len_, want)
                            : f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want)
                                 : (long)read(fd_, buf_.data() + len_, want);
+            if (mm_ && got == 0 && mm_->failed()) std::cerr << "Error: " << mm_->error() << " (gzip input)" << std::endl;
             if (bgzf_ && got == 0 && bgzf_->failed()) std::cerr << "Error: " << bgzf_->error() << " (BGZF input)" << std::endl;
             if (gz_ && got == 0 && gz_->failed()) std::cerr << "Error: " << gz_->error() << " (gzip input)" << std::endl;
             if (got <= 0) { eof_ = true; break; }
@@ -235,6 +240,7 @@ private:
     gzFile f_ = nullptr;
     std::unique_ptr<fastgz::GzReader> gz_;
     std::unique_ptr<fastgz::BgzfParallelReader> bgzf_;
+    std::unique_ptr<fastgz::MultiMemberReader> mm_;
     std::thread inflater_;
     std::atomic<bool> stop_inflater_{false};
     Queue<std::unique_ptr<std::vector<char>>> chunks_{4};

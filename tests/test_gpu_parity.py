@@ -394,7 +394,7 @@ def test_tgsf_allreduce_sums_context_blocks():
             e.close()
 
 
-@pytest.mark.parametrize("seed", list(range(12)))
+@pytest.mark.parametrize("seed", list(range(32)))
 def test_randomised_parameters_vs_oracle(seed):
     """Parameter fuzz: adapter sets with mixed word counts, every threshold, both k-mer key widths,
     the wide (global-atomic) 5'/3' tables, FASTA input, discard, tiny and huge trims."""
@@ -438,7 +438,7 @@ def test_randomised_parameters_vs_oracle(seed):
         tail_trim=int(rng.choice([0, 0, 3, 120])), end_len=int(rng.choice([20, 150, 400])),
         end_match_len=int(rng.choice([1, 4, 15, 40])), mid_match_len=int(rng.choice([10, 20, 35, 60])),
         extra_len=int(rng.choice([0, 50, 200])), end_sim=end_sim, mid_sim=mid_sim,
-        kmer=int(rng.choice([5, 11, 15, 16, 21, 31])), min_repeat=int(rng.choice([0, 0, 3, 30])),
+        kmer=int(rng.choice([5, 9, 11, 12, 13, 15, 16, 21, 31])), min_repeat=int(rng.choice([0, 0, 3, 30, 300])),
         qtype=0 if fasta else 33, discard=bool(rng.random() < 0.3), adapters=ads, max_read_len=10000)
     _compare(params, batch)
 

@@ -388,3 +388,51 @@ def test_own_inflate_matches_zlib(tmp_path):
         zz[pos] ^= 0x55
         check(bytes(zz), ("corrupt", pos))
     check(bytes(z[:len(z) // 2]), "truncated")
+
+
+def test_speculative_multi_member_gzip_equals_sequential_decode(tmp_path):
+    """fastgz::MultiMemberReader (cat-ed .fastq.gz files): spans between guessed member headers are decoded
+    in parallel and accepted only as an unbroken chain from offset 0; a header-like byte string inside a
+    stored block, a corrupt member and trailing padding must give exactly the sequential decoder's bytes
+    (falling back to streaming where the chain breaks)."""
+    import gzip
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "mm_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "multimember_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(2)
+    recs = []
+    for i in range(2000):
+        ln = int(rng.integers(100, 30000))
+        recs.append(b"@r%d\n" % i + rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), ln).tobytes() + b"\n+\n" +
+                    rng.integers(33, 75, ln).astype(np.uint8).tobytes() + b"\n")
+    raw = b"".join(recs)  # ~60 MB -> ~30 MB compressed: several 8 MB spans
+    step = len(raw) // 7 + 1
+    multi = b"".join(gzip.compress(raw[i:i + step], 1) for i in range(0, len(raw), step))
+    path = str(tmp_path / "mm.gz")
+
+    def run(blob, threads=4):
+        with open(path, "wb") as f:
+            f.write(blob)
+        r = subprocess.run([exe, path, str(threads)], capture_output=True, text=True)
+        assert r.returncode == 0, (r.stdout, r.stderr)
+        w = r.stdout.split()
+        return dict(size=int(w[1]), failed=int(w[4]), fallback=int(w[6]), multi=int(w[8]))
+
+    r = run(multi)
+    assert r == dict(size=len(raw), failed=0, fallback=0, multi=1)
+    assert run(gzip.compress(raw[:20_000_000], 1))["multi"] == 0           # single member: streaming path is chosen
+    tiny = b"".join(gzip.compress(raw[i:i + 20000], 1) for i in range(0, 12_000_000, 20000))
+    assert run(tiny, 3) == dict(size=12_000_000, failed=0, fallback=0, multi=1)
+    fake = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + b"junk" * 8        # looks like a member header
+    c = zlib.compressobj(0, zlib.DEFLATED, 31)                             # stored blocks keep it verbatim
+    m1 = c.compress(raw[:9_000_000] + fake + raw[9_000_000:12_000_000]) + c.flush()
+    r = run(m1 + gzip.compress(raw[12_000_000:30_000_000], 1) + gzip.compress(raw[30_000_000:40_000_000], 1))
+    assert r["fallback"] == 1 and r["failed"] == 0 and r["size"] == 40_000_000 + len(fake)
+    bad = bytearray(multi)
+    bad[len(multi) // 2] ^= 0x20
+    r = run(bytes(bad))
+    assert r["failed"] == 1 and r["fallback"] == 1
+    assert run(multi + b"\0" * 100) == dict(size=len(raw), failed=0, fallback=0, multi=1)
