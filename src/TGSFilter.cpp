@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cctype>
 #include <chrono>
 #include <cstdint>
@@ -23,6 +24,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <iostream>
 #include <string>
 #include <thread>
@@ -505,9 +507,14 @@ int main(int argc, char **argv) {
     ingest::BatchPool batch_pool;
     std::deque<std::unique_ptr<ingest::RawBatch>> pending;
     bool input_done = false;
+    uint64_t pending_bytes = 0;
+    const uint64_t prepass_budget = (uint64_t)((getenv("TGSF_PREPASS_BUFFER_MB") ? atof(getenv("TGSF_PREPASS_BUFFER_MB")) : 24576.0) * 1048576.0);
     std::thread reader;
     std::unique_ptr<ingest::ParallelReader> preader; // plain files: parallel chunk parser
     auto next_parsed = [&]() { return preader ? preader->pop() : parsed.pop(); };
+    std::atomic<bool> reader_stop{false};
+    std::function<bool()> start_readers;
+    bool two_pass = false; // the pre-pass sample did not fit the buffer budget: the main pass re-reads the input
     const bool stream_input = P.Filter || P.OnlyQC;
     if (stream_input) {
         { gzFile probe = gzopen(P.InFile.c_str(), "rb"); if (!probe) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; } gzclose(probe); }
@@ -516,14 +523,18 @@ int main(int argc, char **argv) {
         const bool init_first = getenv("TGSF_INIT_FIRST") != nullptr;
         auto warm_up = [&]() { Timer tw; void *warm = nullptr; if (tgsf_host_alloc(&warm, 1 << 20) == TGSF_OK) tgsf_host_free(warm); tlog("  CUDA context warm-up", tw.lap()); };
         if (init_first) warm_up();
-        if (!ingest::ParallelReader::is_gzip(P.InFile) && !getenv("TGSF_SERIAL_READER")) {
-            const int hw = (int)std::thread::hardware_concurrency();
-            const int nthr = getenv("TGSF_PARSE_THREADS") ? atoi(getenv("TGSF_PARSE_THREADS")) : std::max(1, std::min(8, hw - 2));
-            preader.reset(new ingest::ParallelReader(P.InFile, has_qual, 2 * batch_bases, nthr, &batch_pool));
-            if (!preader->ok()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
-        } else {
-            reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool);
-        }
+        start_readers = [&]() -> bool {
+            if (!ingest::ParallelReader::is_gzip(P.InFile) && !getenv("TGSF_SERIAL_READER")) {
+                const int hw = (int)std::thread::hardware_concurrency();
+                const int nthr = getenv("TGSF_PARSE_THREADS") ? atoi(getenv("TGSF_PARSE_THREADS")) : std::max(1, std::min(8, hw - 2));
+                preader.reset(new ingest::ParallelReader(P.InFile, has_qual, 2 * batch_bases, nthr, &batch_pool));
+                return preader->ok();
+            }
+            reader_stop.store(false);
+            reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool, &reader_stop);
+            return true;
+        };
+        if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
         if (!init_first) warm_up();
         while (!input_done && seqNum < maxSeq) {
             std::unique_ptr<ingest::RawBatch> rb = next_parsed();
@@ -541,7 +552,30 @@ int main(int argc, char **argv) {
                     if (maxQ < q) maxQ = q;
                 }
             }
-            pending.push_back(std::move(rb));
+            // The sampled reads are kept for the main pass (one pass over the input) while they fit the budget;
+            // beyond it the pre-pass goes on without keeping them and the input is read again, like the
+            // reference does (T.cpp:949-982 then 1845-1916).
+            if (!two_pass) {
+                pending_bytes += rb->bases.size() + rb->quals.size();
+                pending.push_back(std::move(rb));
+                if (pending_bytes > prepass_budget) {
+                    two_pass = true;
+                    for (auto &pb : pending) batch_pool.put(std::move(pb));
+                    pending.clear();
+                }
+            } else {
+                batch_pool.put(std::move(rb));
+            }
+        }
+        if (two_pass) { // restart the input from its beginning
+            if (preader) preader.reset();
+            if (reader.joinable()) {
+                reader_stop.store(true);
+                while (!input_done) { if (!parsed.pop()) input_done = true; }
+                reader.join();
+            }
+            input_done = false;
+            if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
         }
     } else { // -F: only the sample is needed here; DownSampleTask reads the file itself
         FastxReader rd(P.InFile);

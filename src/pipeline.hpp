@@ -281,7 +281,7 @@ private:
 };
 
 inline void reader_main(const std::string &path, bool fastq, uint64_t batch_bases,
-                        Queue<std::unique_ptr<RawBatch>> *out, BatchPool *pool) {
+                        Queue<std::unique_ptr<RawBatch>> *out, BatchPool *pool, const std::atomic<bool> *stop = nullptr) {
     FastParser ps(path, fastq);
     auto fresh = [&]() {
         std::unique_ptr<RawBatch> nb = pool->get();
@@ -299,9 +299,10 @@ inline void reader_main(const std::string &path, bool fastq, uint64_t batch_base
         if (b->bases.size() >= batch_bases) {
             out->push(std::move(b));
             b = fresh();
+            if (stop && stop->load()) break; // the consumer restarts the input (two-pass mode)
         }
     }
-    if (b->n()) out->push(std::move(b));
+    if (b->n() && !(stop && stop->load())) out->push(std::move(b));
     out->push(nullptr);
 }
 

@@ -638,3 +638,20 @@ def test_host_cli_two_gpus_equals_one(cfg, args, monkeypatch):
     assert rc1 == 0 and rc2 == 0, (err1, err2)
     assert out1 == out2 and len(out1) > 0
     assert _info(err1) == _info(err2)
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_host_cli_two_pass_mode_equals_single_pass(gz, monkeypatch):
+    """When the pre-pass sample does not fit the host buffer budget the CLI drops the buffered batches and
+    reads the input a second time (like the reference): records, INFO lines must not change."""
+    import gzip
+    batch = synth.make_config(2, 500, max_len=40000)
+    fq = batch.to_fastq()
+    blob, name = (gzip.compress(fq, 1), "in.fq.gz") if gz else (fq, "in.fq")
+    monkeypatch.setenv("TGSF_BATCH_MB", "1")
+    rc1, out1, err1 = _run_host_cli(["-x", "ont"], blob, in_name=name)
+    monkeypatch.setenv("TGSF_PREPASS_BUFFER_MB", "3")
+    rc2, out2, err2 = _run_host_cli(["-x", "ont"], blob, in_name=name)
+    assert rc1 == 0 and rc2 == 0, (err1, err2)
+    assert out1 == out2 and len(out1) > 0
+    assert _info(err1) == _info(err2)
