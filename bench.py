@@ -129,7 +129,34 @@ def gen_workload_gpu(config: int, n_reads: int, seed: int, device):
         sel = np.nonzero((u >= 0.030) & (u < 0.033))[0]
         pos = (300 + rng.random(len(sel)) * (lens[sel] - 700)).astype(np.int64)
         plant(sel, pos, V, VL, rng.integers(0, 512, len(sel)))
-    elif config == 4:
+    if config == 5:
+        # 30 % of reads carry a 6-12 kb tandem repeat (unit 50-500 bp, 1 % error; substitutions only here,
+        # tgsfilter_b200.synth also plants indels), so that repeatLen straddles the -p 5000 bound
+        sel = np.nonzero(rng.random(n_reads) < 0.30)[0]
+        unit_len = rng.integers(50, 501, len(sel))
+        span = np.minimum(rng.integers(6000, 12001, len(sel)), lens[sel] - 200)
+        ok = span > unit_len
+        sel, unit_len, span = sel[ok], unit_len[ok], span[ok]
+        pos = (100 + rng.random(len(sel)) * np.maximum(1, lens[sel] - span - 150)).astype(np.int64)
+        pool = torch.randint(0, 4, (1 << 22,), dtype=torch.uint8, device=device, generator=g)
+        pool = 65 + 2 * pool + 2 * (pool >= 2).to(torch.uint8) + 11 * (pool == 3).to(torch.uint8)
+        unit_off = rng.integers(0, (1 << 22) - 512, len(sel))
+        step = 20000
+        for lo in range(0, len(sel), step):
+            hi = min(len(sel), lo + step)
+            sp = torch.from_numpy(span[lo:hi]).to(device)
+            first = torch.cumsum(sp, 0) - sp
+            rid = torch.repeat_interleave(torch.arange(hi - lo, device=device), sp)
+            j = torch.arange(int(sp.sum().item()), device=device) - first[rid]
+            ul = torch.from_numpy(unit_len[lo:hi]).to(device)[rid]
+            uo = torch.from_numpy(unit_off[lo:hi]).to(device)[rid]
+            val = pool[uo + j % ul]
+            err = torch.rand(val.shape, device=device, generator=g) < 0.01
+            val = torch.where(err, pool[(uo + j * 7 + 13) % (1 << 22)], val)
+            dest = (d_off[torch.from_numpy(sel[lo:hi]).to(device)] + torch.from_numpy(pos[lo:hi]).to(device))[rid] + j
+            bases[dest] = val
+            del sp, first, rid, j, ul, uo, val, err, dest
+    if config == 4:
         k = 12
         r = np.arange(n_reads)
         J = torch.arange(k, device=device)[None, :]
