@@ -322,9 +322,8 @@ static __device__ u32 kmer_tag_count(const u32 *tile, u32 *table, uint16_t *pend
         const u32 total = s_cnt[0];
         if (total == 0) return mine;
         if (total <= cap_a) { // compact the pending positions into list_a
-            const u32 n_iter = (n_scan + blockDim.x - 1) / blockDim.x;
-            for (u32 it = 0; it < n_iter; ++it) {
-                const u32 w = it * blockDim.x + threadIdx.x;
+            for (u32 w0 = (threadIdx.x & ~31u); w0 < n_scan; w0 += KMER_SB_THREADS) { // warp-uniform trip count
+                const u32 w = w0 + lane;
                 u32 m = (w < n_scan) ? pend[w] : 0u;
                 const u32 c = __popc(m);
                 u32 incl = c;
@@ -353,18 +352,34 @@ static __device__ u32 kmer_tag_count(const u32 *tile, u32 *table, uint16_t *pend
     u32 ci = 0;
     __syncthreads(); // list_a complete; pend[] is dead from here on
     while (n_list) {
+        if (n_list <= 64) {
+            // tail: the few keys left are compared pairwise (a round costs ~100 issue slots in every warp of
+            // the CTA however short the list is, and each round only resolves ~80 % of it)
+            u32 key = 0;
+            if (threadIdx.x < n_list) {
+                const u32 pos = cur[threadIdx.x], w = pos >> 4;
+                key = __funnelshift_l(tile[w + 1], tile[w], 2 * (pos & 15u)) >> sh;
+                nxt[threadIdx.x] = key;
+            }
+            __syncthreads();
+            if (threadIdx.x < n_list) {
+                bool dup = false;
+                for (u32 j = 0; j < threadIdx.x; ++j) dup |= nxt[j] == key;
+                mine += dup ? 0u : 1u;
+            }
+            break;
+        }
         ++round;
         const u32 mult = 0x9E3779B1u + 0x3C6EF372u * round;
         if (threadIdx.x == 0) s_cnt[ci] = 0;
-        for (u32 i = threadIdx.x; i < n_list; i += blockDim.x) {
+        for (u32 i = threadIdx.x; i < n_list; i += KMER_SB_THREADS) {
             const u32 pos = cur[i], w = pos >> 4;
             const u32 mixed = kmer_mix(__funnelshift_l(tile[w + 1], tile[w], 2 * (pos & 15u)) >> sh, mult, keymask, half);
             table[mixed & (KMER_TAG_SLOTS - 1)] = kmer_tag_of(mixed, pos);
         }
         __syncthreads();
-        const u32 n_iter = (n_list + blockDim.x - 1) / blockDim.x;
-        for (u32 it = 0; it < n_iter; ++it) {
-            const u32 i = it * blockDim.x + threadIdx.x;
+        for (u32 i0 = (threadIdx.x & ~31u); i0 < n_list; i0 += KMER_SB_THREADS) { // warp-uniform trip count
+            const u32 i = i0 + lane;
             bool lost = false;
             u32 pos = 0;
             if (i < n_list) {
