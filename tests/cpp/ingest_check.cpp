@@ -36,7 +36,7 @@ int main(int argc, char **argv) {
     if (!only || !strcmp(only, "serial")) {
         ingest::Queue<std::unique_ptr<ingest::RawBatch>> q(4);
         ingest::BatchPool pool;
-        std::thread t(ingest::reader_main, path, fastq, chunk, &q, &pool);
+        std::thread t([&] { ingest::reader_main(path, fastq, chunk, &q, &pool); });
         while (auto rb = q.pop()) { a.add(*rb); pool.put(std::move(rb)); }
         t.join();
     }
