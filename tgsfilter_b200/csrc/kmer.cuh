@@ -43,7 +43,7 @@ k_kmer(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pi
         if (pc.status != TGSF_PIECE_EMIT) continue;
         const int L = pc.len;
         const int total = L - k + 1;
-        int repeat;
+        int repeat = 0;
         if (total <= 0) {
             repeat = total - 1; // see oracle/tgsf_oracle.c kmer_repeat_len
         } else {
@@ -77,10 +77,9 @@ k_kmer(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pi
             }
             atomicAdd(&s_distinct, mine);
             __syncthreads();
-            repeat = total - (int)s_distinct;
-            __syncthreads();
         }
         if (threadIdx.x == 0) {
+            if (total > 0) repeat = total - (int)*(volatile u32 *)&s_distinct; // thread 0 alone reads and resets it
             pc.repeat_len = repeat;
             if (repeat < P.min_repeat) { // T.cpp:1984-1988
                 pc.status = TGSF_PIECE_SHORT_REPEAT;
@@ -114,7 +113,7 @@ k_kmer_bitmap(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict
         if (pc.status != TGSF_PIECE_EMIT) continue;
         const int L = pc.len;
         const int total = L - k + 1;
-        int repeat;
+        int repeat = 0;
         if (total <= 0) {
             repeat = total - 1;
         } else {
@@ -136,7 +135,6 @@ k_kmer_bitmap(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict
             }
             atomicAdd(&s_distinct, mine);
             __syncthreads();
-            repeat = total - (int)s_distinct;
             if (i0 < i1) { // wipe exactly the words this piece touched
                 u32 km = 0;
                 for (int j = 0; j < k - 1; ++j) km = (km << 2) | base_code(seq[i0 + j]);
@@ -148,6 +146,7 @@ k_kmer_bitmap(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict
             __syncthreads();
         }
         if (threadIdx.x == 0) {
+            if (total > 0) repeat = total - (int)*(volatile u32 *)&s_distinct; // thread 0 alone reads and resets it
             pc.repeat_len = repeat;
             if (repeat < P.min_repeat) { // T.cpp:1984-1988
                 pc.status = TGSF_PIECE_SHORT_REPEAT;
@@ -428,7 +427,7 @@ k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__
         tgsf_piece pc = pieces[pi];
         if (pc.status != TGSF_PIECE_EMIT) continue;
         const int total = pc.len - k + 1;
-        int repeat;
+        int repeat = 0;
         if (total <= 0) {
             repeat = total - 1; // see oracle/tgsf_oracle.c kmer_repeat_len
         } else {
@@ -501,9 +500,9 @@ k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__
             }
             atomicAdd(&s_distinct, mine);
             __syncthreads();
-            repeat = total - (int)s_distinct;
         }
         if (threadIdx.x == 0) {
+            if (total > 0) repeat = total - (int)*(volatile u32 *)&s_distinct; // thread 0 alone reads and resets it
             pc.repeat_len = repeat;
             if (repeat < P.min_repeat) { // T.cpp:1984-1988
                 pc.status = TGSF_PIECE_SHORT_REPEAT;
