@@ -625,6 +625,8 @@ int enqueue_d2h(tgsf_ctx *c, Slot &s) {
     const u32 n = s.B.n_reads;
     CU(cudaMemcpyAsync(s.h_header.p, s.header.p, sizeof(DevHeader), cudaMemcpyDeviceToHost, st));
     if (n) CU(cudaMemcpyAsync(s.h_res.p, s.res.p, (size_t)n * sizeof(tgsf_read_result), cudaMemcpyDeviceToHost, st));
+    // the piece count is only known on the device: copy an optimistic prefix without waiting for it (entries
+    // beyond the count are never read; tgsf_collect fetches the rest if a batch produced more)
     s.h_pieces_copied = std::min<u32>(s.pieces_cap, n + 4096);
     if (s.h_pieces_copied)
         CU(cudaMemcpyAsync(s.h_pieces.p, s.pieces.p, (size_t)s.h_pieces_copied * sizeof(tgsf_piece),
@@ -807,6 +809,8 @@ static int submit_common(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals
             TRY(s.in_bases.ensure((size_t)n_words * 16 + pad));
             TRY(s.in_packed.ensure((size_t)n_words * 4 + pad));
             if (n_bases) {
+                // the unpack kernel reads whole 32-bit words: define the bytes of the last word beyond the copy
+                CU(cudaMemsetAsync((uint8_t *)s.in_packed.p + (n_words - 1) * 4, 0, 4, s.stream));
                 CU(cudaMemcpyAsync(s.in_packed.p, pk->packed, (size_t)((n_bases + 3) / 4), cudaMemcpyHostToDevice, s.stream));
                 k_unpack_bases<<<c->sm_count * 8, 256, 0, s.stream>>>(s.in_packed.as<u32>(), n_words, s.in_bases.as<uint4>());
                 c->launches++;
