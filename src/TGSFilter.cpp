@@ -109,7 +109,7 @@ int usage() {
                  "   --qc         disable all filter, only for quality control \n"
                  "   -f           force FASTA output (discard quality) \n"
                  "   -c   <int>   compression level (0-9) for compressed output [6]\n"
-                 "   -t   <int>   accepted for compatibility (the GPU replaces the worker threads)\n"
+                 "   -t   <int>   host threads for compressing/writing the output [16] (filtering runs on the GPU)\n"
                  "   --gpus <int> number of GPUs to shard batches over [1]\n"
                  "   -h           show help [b200 host of v1.11]\n\n";
     return 1;
