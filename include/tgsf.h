@@ -39,6 +39,8 @@ extern "C" {
 #define TGSF_FLAG_FILTER 1u      /* Para_A24::Filter  (T.cpp:115, cleared by -F / --qc) */
 #define TGSF_FLAG_ONLY_QC 2u     /* Para_A24::OnlyQC  (T.cpp:119) */
 #define TGSF_FLAG_DISCARD_MID 4u /* Para_A24::discard (-D, T.cpp:108) */
+#define TGSF_FLAG_GZ_BLOCKS 8u   /* also deflate-encode every emitted piece on the GPU (tgsf_collect_gz) */
+#define TGSF_FLAG_GZ_FASTA 16u   /* ... as FASTA records (bases only), like -f / FASTA input */
 
 /* All thresholds consumed by the per-read path: the subset of Para_A24 (T.cpp:82-172) that
  * filter_sequence/adapterMap/GetEditDistance read, after the pre-pass has resolved qType, MinQ,
@@ -159,6 +161,21 @@ int tgsf_pack_bases(const uint8_t *bases, uint64_t n, uint8_t *packed, uint64_t 
 /* Same, with the three arrays already resident in this GPU's memory (device pointers). */
 int tgsf_submit_device(tgsf_ctx *ctx, const uint8_t *d_bases, const uint8_t *d_quals,
                        const uint64_t *d_offsets, uint32_t n_reads, uint64_t n_bases);
+/* Deflate blocks of the emitted pieces of the OLDEST outstanding batch (contexts created with
+ * TGSF_FLAG_GZ_BLOCKS; replaces the compression half of DeflateCompress, T.cpp:786-812).  Must be called
+ * before tgsf_collect for that batch.  spans[i] describes piece i of the batch (same order as tgsf_collect's
+ * pieces; bytes == 0 for pieces that are not emitted): blob[offset, offset + bytes) holds, byte aligned,
+ * the dynamic-Huffman blocks of bases + "\n+\n" + qualities + "\n" (FASTA: bases + "\n"), the last one
+ * final.  A gzip member of the record is: 10-byte gzip header, a non-final stored block with the header
+ * line ("@name\n"), these bytes, CRC-32 and ISIZE of the whole record.  blob_cap too small:
+ * TGSF_ERR_CAPACITY with *blob_bytes = required size. */
+typedef struct tgsf_gz_span {
+    uint64_t offset;
+    uint32_t bytes;
+    uint32_t reserved;
+} tgsf_gz_span;
+int tgsf_collect_gz(tgsf_ctx *ctx, uint8_t *blob, uint64_t blob_cap, uint64_t *blob_bytes, tgsf_gz_span *spans,
+                    uint32_t spans_cap, uint32_t *n_spans);
 /* Waits for the oldest outstanding batch and copies its results out.  reads: n_reads entries;
  * pieces: up to pieces_cap entries, *n_pieces receives the number produced (TGSF_ERR_CAPACITY and
  * no copy if it exceeds pieces_cap; call again with a larger array).  reads/pieces may be NULL to

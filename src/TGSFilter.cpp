@@ -705,6 +705,9 @@ int main(int argc, char **argv) {
     tp.extra_len = P.ExtraLen; tp.end_sim = P.EndSim; tp.mid_sim = P.MidSim;
     tp.kmer = P.Kmer; tp.min_repeat = P.MinRepeat; tp.qtype = qType;
     tp.flags = (P.Filter ? TGSF_FLAG_FILTER : 0) | (P.OnlyQC ? TGSF_FLAG_ONLY_QC : 0) | (P.discard ? TGSF_FLAG_DISCARD_MID : 0);
+    // .gz output: the deflate blocks of every record are produced on the GPU (TGSF_GZ_HOST=1: host zlib instead)
+    const bool gz_gpu = P.OUTGZ && !P.Downsample && !P.OnlyQC && !getenv("TGSF_GZ_HOST");
+    if (gz_gpu) tp.flags |= TGSF_FLAG_GZ_BLOCKS | (P.Outfq == 1 ? 0u : TGSF_FLAG_GZ_FASTA);
     std::vector<const uint8_t *> aseq;
     std::vector<int32_t> alen;
     for (const string &a : adapters) { aseq.push_back((const uint8_t *)a.data()); alen.push_back((int32_t)a.size()); }
@@ -754,8 +757,14 @@ int main(int argc, char **argv) {
     //  * gzip output: one member per record like DeflateCompress (T.cpp:786-812), the records of a
     //    batch spread over -t compressor threads, written in order;
     //  * downsampling: the serial path (uncompressed tmp file + record index).
-    struct WriteJob { std::unique_ptr<ingest::RawBatch> rb; std::vector<tgsf_piece> pieces; };
-    struct Emit { uint32_t read, start, len; int pass; };
+    struct WriteJob {
+        std::unique_ptr<ingest::RawBatch> rb;
+        std::vector<tgsf_piece> pieces;
+        std::vector<uint8_t> gz_blob;      // GPU deflate blocks of the batch (gz_gpu)
+        std::vector<tgsf_gz_span> gz_spans; // per piece
+        bool gz_ok = false;
+    };
+    struct Emit { uint32_t read, start, len; int pass; uint32_t piece; };
     ingest::Queue<std::unique_ptr<WriteJob>> to_write(4);
     const int out_threads = std::max(1, std::min(P.n_thread, (int)std::thread::hardware_concurrency()));
     fflush(out);
@@ -779,10 +788,11 @@ int main(int argc, char **argv) {
             renamed.clear();
             uint32_t last = UINT32_MAX;
             int pass = 1;
-            for (const tgsf_piece &p : job->pieces) { // T.cpp:1976-2059
+            for (size_t pi = 0; pi < job->pieces.size(); ++pi) { // T.cpp:1976-2059
+                const tgsf_piece &p = job->pieces[pi];
                 if ((uint32_t)p.read != last) { last = (uint32_t)p.read; pass = 1; }
                 if (p.status != TGSF_PIECE_EMIT) continue;
-                emits.push_back(Emit{last, (uint32_t)p.start, (uint32_t)p.len, pass});
+                emits.push_back(Emit{last, (uint32_t)p.start, (uint32_t)p.len, pass, (uint32_t)pi});
                 pass++;
                 cleanNum++;
                 cleanBases += (uint64_t)p.len;
@@ -836,7 +846,61 @@ int main(int argc, char **argv) {
                     while (k + 1 < K) { cut[(size_t)++k] = emits.size(); bytes_before[(size_t)k] = raw; }
                     bytes_before[(size_t)K] = raw;
                 }
-                if (gz_now) {
+                if (gz_now && job->gz_ok) {
+                    // members around the GPU's deflate blocks: gzip header | stored block with the header line |
+                    // blocks | CRC-32, ISIZE (include/tgsf.h, tgsf_collect_gz); CRC and copies spread over -t threads
+                    bufs.resize((size_t)K);
+                    auto assemble_range = [&](int k) {
+                        string &dst = bufs[(size_t)k];
+                        dst.clear();
+                        static const unsigned char kHdr[10] = {0x1f, 0x8b, 8, 0, 0, 0, 0, 0, 0, 0xff};
+                        for (size_t i = cut[(size_t)k]; i < cut[(size_t)k + 1]; ++i) {
+                            const Emit &e = emits[i];
+                            const tgsf_gz_span &sp = job->gz_spans[e.piece];
+                            const Bytef *sq = (const Bytef *)b.bases.data() + b.offsets[e.read] + e.start;
+                            const size_t hl = nm[i]->size() + 2;
+                            string head;
+                            head += P.Outfq == 1 ? '@' : '>';
+                            head += *nm[i];
+                            head += '\n';
+                            uLong crc = crc32(0L, (const Bytef *)head.data(), (uInt)hl);
+                            crc = crc32(crc, sq, (uInt)e.len);
+                            uint64_t isize = hl + e.len + 1;
+                            if (P.Outfq == 1) {
+                                crc = crc32(crc, (const Bytef *)"\n+\n", 3);
+                                crc = crc32(crc, (const Bytef *)b.quals.data() + b.offsets[e.read] + e.start, (uInt)e.len);
+                                isize += 2 + e.len + 1;
+                            }
+                            crc = crc32(crc, (const Bytef *)"\n", 1);
+                            dst.append((const char *)kHdr, 10);
+                            // stored blocks hold at most 65535 bytes: header lines are far shorter, but stay correct
+                            size_t done = 0;
+                            while (done < hl) {
+                                const size_t n = std::min<size_t>(hl - done, 65535);
+                                const unsigned char sb[5] = {0, (unsigned char)n, (unsigned char)(n >> 8), (unsigned char)~n, (unsigned char)(~n >> 8)};
+                                dst.append((const char *)sb, 5);
+                                dst.append(head.data() + done, n);
+                                done += n;
+                            }
+                            dst.append((const char *)job->gz_blob.data() + sp.offset, sp.bytes);
+                            const uint32_t tr[2] = {(uint32_t)crc, (uint32_t)isize};
+                            dst.append((const char *)tr, 8);
+                        }
+                    };
+                    std::vector<std::thread> th;
+                    for (int k = 1; k < K; ++k) th.emplace_back(assemble_range, k);
+                    assemble_range(0);
+                    for (auto &t : th) t.join();
+                    for (int k = 0; k < K; ++k) {
+                        const string &d = bufs[(size_t)k];
+                        size_t done = 0;
+                        while (done < d.size()) {
+                            const ssize_t w = write(out_fd, d.data() + done, d.size() - done);
+                            if (w <= 0) { cerr << "Error: write failed" << endl; exit(-1); }
+                            done += (size_t)w;
+                        }
+                    }
+                } else if (gz_now) {
                     bufs.resize((size_t)K);
                     // Per-record members hold no cross-record matches, and on noisy long reads zlib's match
                     // search at the default strategy yields files no smaller than run-length + Huffman coding
@@ -966,6 +1030,19 @@ int main(int argc, char **argv) {
         rr.resize(n);
         job->pieces.resize((size_t)n + 4096);
         uint32_t np = 0;
+        if (gz_gpu) { // before tgsf_collect, which retires the batch
+            uint64_t nb = 0;
+            uint32_t ns = 0;
+            job->gz_blob.resize((size_t)(sl.rb->bases.size() * (has_qual && P.Outfq == 1 ? 1.0 : 0.5) + (1u << 20)));
+            job->gz_spans.resize((size_t)n + 4096);
+            int grc = tgsf_collect_gz(c, job->gz_blob.data(), job->gz_blob.size(), &nb, job->gz_spans.data(), (uint32_t)job->gz_spans.size(), &ns);
+            if (grc == TGSF_ERR_CAPACITY) {
+                job->gz_blob.resize((size_t)nb + 16);
+                job->gz_spans.resize((size_t)ns + 16);
+                grc = tgsf_collect_gz(c, job->gz_blob.data(), job->gz_blob.size(), &nb, job->gz_spans.data(), (uint32_t)job->gz_spans.size(), &ns);
+            }
+            job->gz_ok = grc == TGSF_OK; // otherwise (region-pool re-run) this batch is compressed on the host
+        }
         int rc = tgsf_collect(c, rr.data(), n, job->pieces.data(), (uint32_t)job->pieces.size(), &np);
         if (rc == TGSF_ERR_CAPACITY && np > job->pieces.size()) {
             job->pieces.resize(np);

@@ -355,16 +355,32 @@ def test_host_cli_vs_reference_cli(cfg, n, args):
     assert _info(h_err) == _info(r_err)
 
 
-def test_host_cli_gzip_in_and_out_roundtrip():
+@pytest.mark.parametrize("mode", ["gpu_blocks", "host_zlib", "fasta_out", "small_batches"])
+def test_host_cli_gzip_in_and_out_roundtrip(mode, monkeypatch):
+    """.gz output: one gzip member per record; the deflate blocks come from the GPU (default) or from host zlib
+    (TGSF_GZ_HOST=1).  Either way the decompressed file equals the plain output; the reference CLI must be able
+    to read it back (FastxReader's multi-member inflate, T.cpp:601-640)."""
     import gzip
     import ref_lib
-    batch = synth.make_config(2, 120, max_len=40000)
+    batch = synth.make_config(2, 160, max_len=40000)
     fq = batch.to_fastq()
-    rc, out_plain, _ = _run_host_cli(["-x", "ont"], fq)
-    rc2, out_gz, err = _run_host_cli(["-x", "ont", "-c", "4"], gzip.compress(fq), in_name="in.fq.gz",
-                                     out_name="out.fq.gz")
+    extra = ["-f"] if mode == "fasta_out" else []
+    if mode == "host_zlib":
+        monkeypatch.setenv("TGSF_GZ_HOST", "1")
+    if mode == "small_batches":
+        monkeypatch.setenv("TGSF_BATCH_MB", "1")
+    rc, out_plain, _ = _run_host_cli(["-x", "ont"] + extra, fq, out_name="out.fa" if extra else "out.fq")
+    rc2, out_gz, err = _run_host_cli(["-x", "ont", "-c", "4"] + extra, gzip.compress(fq), in_name="in.fq.gz",
+                                     out_name="out.fa.gz" if extra else "out.fq.gz")
     assert rc == 0 and rc2 == 0, err
+    assert len(out_plain) > 100000
     assert gzip.decompress(out_gz) == out_plain  # one gzip member per record, same bytes inside
+    assert out_gz.count(b"\x1f\x8b\x08") >= out_plain.count(b"\n") // 4
+    if ref_lib.available() and mode in ("gpu_blocks", "small_batches"):
+        # the reference reads our members: --qc over the compressed output reports the same totals as over the plain one
+        r1 = ref_lib.run_cli(["--qc"], out_plain, in_name="x.fq", out_name=None)
+        r2 = ref_lib.run_cli(["--qc"], out_gz, in_name="x.fq.gz", out_name=None)
+        assert _info(r1[2]) == _info(r2[2]) and len(_info(r1[2])) > 0
 
 
 def test_tgsf_allreduce_sums_context_blocks():
@@ -655,3 +671,69 @@ def test_host_cli_two_pass_mode_equals_single_pass(gz, monkeypatch):
     assert rc1 == 0 and rc2 == 0, (err1, err2)
     assert out1 == out2 and len(out1) > 0
     assert _info(err1) == _info(err2)
+
+
+def _gz_members(batch, pieces, blob, spans, fastq):
+    """Assemble gzip members around the GPU's deflate blocks exactly as src/TGSFilter.cpp does."""
+    import struct
+    import zlib
+    out = []
+    texts = records.format_records(batch, pieces, fastq=fastq)
+    emitted = [i for i in range(len(pieces)) if pieces["status"][i] == 0]
+    assert len(texts) == len(emitted)
+    for (text, name, _ln), i in zip(texts, emitted):
+        head = (b"@" if fastq else b">") + name + b"\n"
+        off, nb = int(spans["offset"][i]), int(spans["bytes"][i])
+        assert nb > 0
+        body = blob[off:off + nb].tobytes()
+        out.append(b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\xff" + b"\x00" + struct.pack("<HH", len(head), len(head) ^ 0xFFFF)
+                   + head + body + struct.pack("<II", zlib.crc32(text), len(text) & 0xFFFFFFFF))
+    return out, [t for t, _, _ in texts]
+
+
+@pytest.mark.parametrize("cfg,n,fasta", [(1, 300, False), (2, 200, False), (3, 40, False), (2, 150, True), (5, 200, False)])
+def test_gpu_deflate_blocks_inflate_to_the_records(cfg, n, fasta):
+    """tgsf_collect_gz: the per-piece dynamic-Huffman blocks, wrapped into gzip members, must inflate (zlib) to
+    exactly the records the uncompressed path writes; non-emitted pieces get empty spans."""
+    import gzip
+    batch = synth.make_config(cfg, n, max_len=150000)
+    params = synth.config_params(cfg)
+    if cfg == 5:
+        params.min_repeat = 40
+    params.gz_blocks = True
+    params.gz_fasta = fasta
+    with FilterEngine(params) as eng:
+        eng.submit(batch)
+        blob, spans = eng.collect_gz()
+        reads, pieces = eng.collect()
+    assert len(spans) == len(pieces)
+    assert all(int(spans["bytes"][i]) == 0 for i in range(len(pieces)) if pieces["status"][i] != 0)
+    members, texts = _gz_members(batch, pieces, blob, spans, fastq=not fasta)
+    assert len(members) > 10
+    for m, t in zip(members, texts):
+        assert gzip.decompress(m) == t
+    # concatenated, as written to a .gz file
+    assert gzip.decompress(b"".join(members)) == b"".join(texts)
+    total_in, total_out = sum(len(t) for t in texts), sum(len(m) for m in members)
+    assert total_out < 0.62 * total_in
+
+
+def test_gpu_deflate_blocks_odd_records():
+    # 1-base pieces are impossible (min_len), but homopolymers, N / lower case, all quality bytes and FASTA input are not
+    rng = np.random.default_rng(9)
+    seqs = [b"A" * 3000, b"ACGT" * 1000, bytes(rng.choice(np.frombuffer(b"ACGTNacgtnRY", dtype=np.uint8), 5000)),
+            bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 70001))]
+    quals = [b"#" * 3000, bytes(rng.integers(33, 127, 4000).astype(np.uint8)), bytes(rng.integers(33, 127, 5000).astype(np.uint8)),
+             bytes(rng.integers(33, 60, 70001).astype(np.uint8))]
+    import gzip
+    for with_q in (True, False):
+        batch = synth.pack_reads(seqs, quals if with_q else None)
+        params = FilterParams(min_len=100, min_q=0.0, qtype=33 if with_q else 0, adapters=[], max_read_len=100000, gz_blocks=True)
+        with FilterEngine(params) as eng:
+            eng.submit(batch)
+            blob, spans = eng.collect_gz()
+            reads, pieces = eng.collect()
+        members, texts = _gz_members(batch, pieces, blob, spans, fastq=with_q)
+        assert len(members) == 4
+        for m, t in zip(members, texts):
+            assert gzip.decompress(m) == t

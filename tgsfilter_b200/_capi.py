@@ -22,6 +22,8 @@ TGSF_ERR_CAPACITY = 5
 FLAG_FILTER = 1
 FLAG_ONLY_QC = 2
 FLAG_DISCARD_MID = 4
+FLAG_GZ_BLOCKS = 8
+FLAG_GZ_FASTA = 16
 
 READ_EVALUATED, READ_LOWQ, READ_EMPTY = 0, 1, 2
 PIECE_EMIT, PIECE_SHORT_REPEAT, PIECE_LOWQ, PIECE_QC_ONLY = 0, 1, 2, 3
@@ -111,7 +113,7 @@ ALIGN_RESULT_DTYPE = [("edit_distance", "<i4"), ("n_locations", "<i4"), ("align_
 # every symbol include/tgsf.h declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
     "tgsf_version", "tgsf_last_error", "tgsf_create", "tgsf_destroy", "tgsf_host_alloc",
-    "tgsf_host_free", "tgsf_submit", "tgsf_submit_packed", "tgsf_pack_bases", "tgsf_submit_device", "tgsf_collect", "tgsf_last_timing", "tgsf_last_stage_ms",
+    "tgsf_host_free", "tgsf_submit", "tgsf_submit_packed", "tgsf_pack_bases", "tgsf_submit_device", "tgsf_collect", "tgsf_collect_gz", "tgsf_last_timing", "tgsf_last_stage_ms",
     "tgsf_counter_layout_get", "tgsf_counters", "tgsf_counters_reset", "tgsf_counters_device",
     "tgsf_launch_count", "tgsf_allreduce", "tgsf_prepass", "tgsf_align_hw",
 )

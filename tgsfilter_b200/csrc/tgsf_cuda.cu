@@ -15,6 +15,7 @@
 #include "adapters.cuh"
 #include "common.cuh"
 #include "kmer.cuh"
+#include "gzenc.cuh"
 #include "prepass.cuh"
 #include "regions.cuh"
 #include "scan.cuh"
@@ -181,7 +182,8 @@ struct DevHeader { // small block mirrored to the host with every batch
     u32 status;
     u32 tmp_cursor;  // total pieces
     u32 sort_cursor;
-    u32 pad;
+    u32 gz_overflow; // k_gz_encode ran out of blob space
+    unsigned long long gz_cursor; // bytes of deflate blocks produced
 };
 
 struct Slot {
@@ -199,7 +201,7 @@ struct Slot {
     DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first, chunk_perm, chunk_hist;
     int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
-    DBuf scan_tmp, kmer_bitmaps;
+    DBuf scan_tmp, kmer_bitmaps, gz_blob, gz_spans;
     Scratch scratch;
     u32 pool_cap = 0, pieces_cap = 0, chunks_cap = 0, tiles_cap = 0;
     // host results
@@ -267,7 +269,7 @@ void slot_release(Slot &s) {
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
                     &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
-                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.scratch.buf};
+                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.gz_blob, &s.gz_spans, &s.scratch.buf};
     for (DBuf *b : bufs) b->release();
     s.h_res.release();
     s.h_pieces.release();
@@ -323,6 +325,12 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.pieces.ensure((size_t)s.pieces_cap * sizeof(tgsf_piece)));
     TRY(s.res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
     TRY(s.header.ensure(sizeof(DevHeader)));
+    if (c->P.flags & TGSF_FLAG_GZ_BLOCKS) {
+        // literal-only Huffman coding: <= 9/8 bytes per symbol on average, plus headers and padding per piece
+        const u64 syms = n_bases * ((c->P.flags & TGSF_FLAG_GZ_FASTA) ? 1ull : 2ull);
+        TRY(s.gz_blob.ensure((size_t)(syms + syms / 8 + (u64)s.pieces_cap * 512ull + 4096ull)));
+        TRY(s.gz_spans.ensure((size_t)s.pieces_cap * sizeof(GzSpan)));
+    }
     const size_t scan_words = 4 * (std::max<size_t>(nseg, (size_t)n * A) / SCANB_TILE) + 4096;
     TRY(s.scan_tmp.ensure(scan_words * sizeof(u32)));
     TRY(s.h_res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
@@ -614,6 +622,17 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
         TRY(launch_ends_qc(c, s, s.pieces_cap, s.seg_flag.as<int>(), true));
     } else {
         CU(cudaEventRecord(s.ev_stage[6], st));
+    }
+    if ((P.flags & TGSF_FLAG_GZ_BLOCKS) && !(P.flags & TGSF_FLAG_ONLY_QC)) {
+        // deflate blocks of the emitted pieces (timed with the clean stage)
+        const bool fasta = (P.flags & TGSF_FLAG_GZ_FASTA) || !s.has_qual;
+        const u64 syms = s.n_bases * (fasta ? 1ull : 2ull);
+        const u64 used_cap = std::min<u64>(s.gz_blob.cap, syms + syms / 8 + (u64)s.pieces_cap * 512ull + 4096ull) & ~3ull;
+        CU(cudaMemsetAsync(s.gz_blob.p, 0, (size_t)used_cap, st));
+        k_gz_encode<<<c->sm_count * 6, GZ_THREADS, 0, st>>>(s.B, s.pieces.as<tgsf_piece>(), &H->tmp_cursor, fasta ? 1 : 0,
+                                                          s.gz_blob.as<u32>(), used_cap, &H->gz_cursor,
+                                                          s.gz_spans.as<GzSpan>(), &H->gz_overflow, &H->status);
+        c->launches++;
     }
     CU(cudaEventRecord(s.ev_stage[7], st));
     return check_launch("tail");
@@ -930,6 +949,30 @@ int tgsf_pack_bases(const uint8_t *bases, uint64_t n, uint8_t *packed, uint64_t 
 int tgsf_submit_device(tgsf_ctx *c, const uint8_t *d_bases, const uint8_t *d_quals, const uint64_t *d_offsets,
                        uint32_t n_reads, uint64_t n_bases) {
     return submit_common(c, d_bases, d_quals, (const u64 *)d_offsets, n_reads, n_bases, true);
+}
+
+int tgsf_collect_gz(tgsf_ctx *c, uint8_t *blob, uint64_t blob_cap, uint64_t *blob_bytes, tgsf_gz_span *spans,
+                    uint32_t spans_cap, uint32_t *n_spans) {
+    if (!c || !blob_bytes || !n_spans) { set_err("collect_gz: NULL argument"); return TGSF_ERR_INVALID; }
+    if (!(c->P.flags & TGSF_FLAG_GZ_BLOCKS)) { set_err("context was created without TGSF_FLAG_GZ_BLOCKS"); return TGSF_ERR_STATE; }
+    if (c->outstanding == 0) { set_err("nothing outstanding"); return TGSF_ERR_STATE; }
+    CU(cudaSetDevice(c->device));
+    Slot &s = c->slots[c->tail];
+    CU(cudaEventSynchronize(s.ev_end));
+    const DevHeader *H = (const DevHeader *)s.h_header.p;
+    if (H->status == DEV_STATUS_POOL_OVERFLOW) { // the tail has to be re-run first: tgsf_collect does that
+        set_err("collect_gz: this batch overflowed the region pool; tgsf_collect re-runs it, compress its records on the host");
+        return TGSF_ERR_STATE;
+    }
+    if (H->gz_overflow) { set_err("deflate blob overflow"); return TGSF_ERR_CUDA; }
+    const u32 np = H->tmp_cursor;
+    *blob_bytes = (uint64_t)H->gz_cursor;
+    *n_spans = np;
+    if (H->gz_cursor > blob_cap || np > spans_cap) { set_err("collect_gz: buffers too small"); return TGSF_ERR_CAPACITY; }
+    if (H->gz_cursor) CU(cudaMemcpyAsync(blob, s.gz_blob.p, (size_t)H->gz_cursor, cudaMemcpyDeviceToHost, s.stream));
+    if (np) CU(cudaMemcpyAsync(spans, s.gz_spans.p, (size_t)np * sizeof(tgsf_gz_span), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    return TGSF_OK;
 }
 
 int tgsf_collect(tgsf_ctx *c, tgsf_read_result *reads, uint32_t n_reads, tgsf_piece *pieces, uint32_t pieces_cap,

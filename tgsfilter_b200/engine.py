@@ -161,6 +161,26 @@ class FilterEngine:
         _capi.check(rc, "tgsf_collect")
         return reads[:n], pieces[:npieces.value]
 
+    def collect_gz(self):
+        """Deflate blocks of the oldest outstanding batch (params.gz_blocks); call before collect().
+        Returns (blob bytes as uint8 array, spans structured array with offset/bytes per piece)."""
+        if not self._inflight:
+            raise RuntimeError("collect_gz() without an outstanding batch")
+        n, _keep = self._inflight[0]
+        span_dtype = np.dtype([("offset", "<u8"), ("bytes", "<u4"), ("reserved", "<u4")])
+        blob = np.zeros(1 << 20, dtype=np.uint8)
+        spans = np.zeros(n + 4096, dtype=span_dtype)
+        nb, ns = C.c_uint64(0), C.c_uint32(0)
+        rc = self._lib.tgsf_collect_gz(self._ctx, blob.ctypes.data, blob.size, C.byref(nb), spans.ctypes.data,
+                                       spans.size, C.byref(ns))
+        if rc == _capi.TGSF_ERR_CAPACITY:
+            blob = np.zeros(max(int(nb.value), 1), dtype=np.uint8)
+            spans = np.zeros(max(int(ns.value), 1), dtype=span_dtype)
+            rc = self._lib.tgsf_collect_gz(self._ctx, blob.ctypes.data, blob.size, C.byref(nb), spans.ctypes.data,
+                                           spans.size, C.byref(ns))
+        _capi.check(rc, "tgsf_collect_gz")
+        return blob[:nb.value], spans[:ns.value]
+
     def run(self, batch):
         self.submit(batch)
         return self.collect()

@@ -79,6 +79,8 @@ class FilterParams:
     filter: bool = True
     only_qc: bool = False
     discard: bool = False          # -D
+    gz_blocks: bool = False        # also deflate-encode the emitted pieces on the GPU (tgsf_collect_gz)
+    gz_fasta: bool = False         # ... as FASTA records
     adapters: Sequence[bytes] = ()
     max_read_len: int = 0
     n_slots: int = 0
@@ -97,7 +99,9 @@ class FilterParams:
     def flags(self) -> int:
         return ((_capi.FLAG_FILTER if self.filter else 0)
                 | (_capi.FLAG_ONLY_QC if self.only_qc else 0)
-                | (_capi.FLAG_DISCARD_MID if self.discard else 0))
+                | (_capi.FLAG_DISCARD_MID if self.discard else 0)
+                | (_capi.FLAG_GZ_BLOCKS if self.gz_blocks else 0)
+                | (_capi.FLAG_GZ_FASTA if self.gz_fasta else 0))
 
     def to_c(self):
         """Returns (tgsf_params struct, keep-alive objects)."""
