@@ -26,6 +26,7 @@
 #include <deque>
 #include <functional>
 #include <iostream>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -760,10 +761,32 @@ int main(int argc, char **argv) {
     struct WriteJob {
         std::unique_ptr<ingest::RawBatch> rb;
         std::vector<tgsf_piece> pieces;
-        std::vector<uint8_t> gz_blob;      // GPU deflate blocks of the batch (gz_gpu)
+        uint8_t *gz_blob = nullptr;        // GPU deflate blocks of the batch (gz_gpu): pinned, recycled through gz_pool
+        size_t gz_cap = 0;
         std::vector<tgsf_gz_span> gz_spans; // per piece
         bool gz_ok = false;
     };
+    struct PinnedPool { // pinned host buffers for the deflate blobs (a pageable target costs page faults + a staged copy)
+        std::mutex m;
+        std::vector<std::pair<uint8_t *, size_t>> free_;
+        std::pair<uint8_t *, size_t> get(size_t need) {
+            {
+                std::lock_guard<std::mutex> lk(m);
+                for (size_t i = 0; i < free_.size(); ++i)
+                    if (free_[i].second >= need) { auto r = free_[i]; free_.erase(free_.begin() + (long)i); return r; }
+                if (!free_.empty()) { tgsf_host_free(free_.back().first); free_.pop_back(); }
+            }
+            void *p = nullptr;
+            const size_t cap = need + need / 4;
+            if (tgsf_host_alloc(&p, cap) != TGSF_OK) return {nullptr, 0};
+            return {(uint8_t *)p, cap};
+        }
+        void put(uint8_t *p, size_t cap) {
+            if (!p) return;
+            std::lock_guard<std::mutex> lk(m);
+            free_.emplace_back(p, cap);
+        }
+    } gz_pool;
     struct Emit { uint32_t read, start, len; int pass; uint32_t piece; };
     ingest::Queue<std::unique_ptr<WriteJob>> to_write(4);
     const int out_threads = std::max(1, std::min(P.n_thread, (int)std::thread::hardware_concurrency()));
@@ -882,7 +905,7 @@ int main(int argc, char **argv) {
                                 dst.append(head.data() + done, n);
                                 done += n;
                             }
-                            dst.append((const char *)job->gz_blob.data() + sp.offset, sp.bytes);
+                            dst.append((const char *)job->gz_blob + sp.offset, sp.bytes);
                             const uint32_t tr[2] = {(uint32_t)crc, (uint32_t)isize};
                             dst.append((const char *)tr, 8);
                         }
@@ -1016,6 +1039,7 @@ int main(int argc, char **argv) {
                 }
             }
             batch_pool.put(std::move(job->rb));
+            gz_pool.put(job->gz_blob, job->gz_cap);
         }
     });
 
@@ -1033,15 +1057,22 @@ int main(int argc, char **argv) {
         if (gz_gpu) { // before tgsf_collect, which retires the batch
             uint64_t nb = 0;
             uint32_t ns = 0;
-            job->gz_blob.resize((size_t)(sl.rb->bases.size() * (has_qual && P.Outfq == 1 ? 1.0 : 0.5) + (1u << 20)));
+            auto pb = gz_pool.get((size_t)(sl.rb->bases.size() * (has_qual && P.Outfq == 1 ? 1.0 : 0.5) + (1u << 20)));
+            job->gz_blob = pb.first;
+            job->gz_cap = pb.second;
             job->gz_spans.resize((size_t)n + 4096);
-            int grc = tgsf_collect_gz(c, job->gz_blob.data(), job->gz_blob.size(), &nb, job->gz_spans.data(), (uint32_t)job->gz_spans.size(), &ns);
+            int grc = job->gz_blob ? tgsf_collect_gz(c, job->gz_blob, job->gz_cap, &nb, job->gz_spans.data(), (uint32_t)job->gz_spans.size(), &ns)
+                                   : TGSF_ERR_NOMEM;
             if (grc == TGSF_ERR_CAPACITY) {
-                job->gz_blob.resize((size_t)nb + 16);
+                gz_pool.put(job->gz_blob, job->gz_cap);
+                pb = gz_pool.get((size_t)nb + 16);
+                job->gz_blob = pb.first;
+                job->gz_cap = pb.second;
                 job->gz_spans.resize((size_t)ns + 16);
-                grc = tgsf_collect_gz(c, job->gz_blob.data(), job->gz_blob.size(), &nb, job->gz_spans.data(), (uint32_t)job->gz_spans.size(), &ns);
+                grc = job->gz_blob ? tgsf_collect_gz(c, job->gz_blob, job->gz_cap, &nb, job->gz_spans.data(), (uint32_t)job->gz_spans.size(), &ns)
+                                   : TGSF_ERR_NOMEM;
             }
-            job->gz_ok = grc == TGSF_OK; // otherwise (region-pool re-run) this batch is compressed on the host
+            job->gz_ok = grc == TGSF_OK; // otherwise (region-pool re-run, no pinned memory) the host compresses this batch
         }
         int rc = tgsf_collect(c, rr.data(), n, job->pieces.data(), (uint32_t)job->pieces.size(), &np);
         if (rc == TGSF_ERR_CAPACITY && np > job->pieces.size()) {

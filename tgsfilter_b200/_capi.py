@@ -145,6 +145,7 @@ def load() -> C.CDLL:
     lib.tgsf_pack_bases.argtypes = [u8p, C.c_uint64, u8p, u64p, u8p, C.c_uint64, C.POINTER(C.c_uint64)]
     lib.tgsf_submit_device.argtypes = [vp, u8p, u8p, u64p, C.c_uint32, C.c_uint64]
     lib.tgsf_collect.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]
+    lib.tgsf_collect_gz.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.tgsf_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.tgsf_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.tgsf_counter_layout_get.argtypes = [vp, C.POINTER(CounterLayout)]
