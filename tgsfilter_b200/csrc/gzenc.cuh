@@ -25,8 +25,8 @@ struct GzSpan { // per piece, same index as the pieces array
     u32 reserved;
 };
 
-// bits [0, n) of v (n <= 32) at absolute bit position `bit` of a zero-initialised blob; `own_lo`/`own_hi`: first and
-// last 32-bit word index this thread may write without atomics (it owns every word strictly inside its bit range)
+// LSB-first bit output of one thread into its bit range of a zero-initialised blob: 32-bit words that lie completely
+// inside the range are written with plain stores, the first and the last (shared with the neighbours) with atomicOr
 struct GzBitOut {
     u32 *words;
     u64 acc;     // pending bits
