@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <algorithm>
 #include <vector>
 
 static void encode_block(GzBitWriter &w, const uint8_t *const *parts, const size_t *lens, int nparts, bool final_block) {
@@ -55,8 +56,30 @@ static std::string member(const std::string &name, const std::string &seq, const
     return std::string((const char *)out.data(), pos);
 }
 
+// code lengths for Fibonacci-like frequencies would exceed the limit: the builder must stay within it and
+// still return a complete prefix code (Kraft sum exactly 1)
+static int selftest() {
+    for (int limit : {15, 7}) {
+        for (int n : {2, 3, 19, 30, 60, 257}) {
+            std::vector<uint32_t> freq(n), scratch(5 * n + 8);
+            uint64_t a = 1, b = 1;
+            for (int i = 0; i < n; ++i) { freq[i] = (uint32_t)std::min<uint64_t>(a, 0x7fffffff); const uint64_t c = a + b; a = b; b = c; }
+            std::vector<uint8_t> len(n);
+            if ((1 << limit) < n) continue; // not representable at all
+            gz_huff_lengths(freq.data(), n, limit, len.data(), scratch.data());
+            double kraft = 0;
+            int mx = 0;
+            for (int i = 0; i < n; ++i) { if (!len[i]) return 1; kraft += 1.0 / (double)(1u << len[i]); mx = std::max<int>(mx, len[i]); }
+            if (mx > limit || kraft != 1.0) { fprintf(stderr, "selftest: n=%d limit=%d max=%d kraft=%f\n", n, limit, mx, kraft); return 1; }
+        }
+    }
+    printf("selftest ok\n");
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc < 2) return 2;
+    if (std::string(argv[1]) == "--selftest") return selftest();
     const bool fasta = argc > 2 && atoi(argv[2]);
     FILE *f = fopen(argv[1], "rb");
     if (!f) return 3;

@@ -436,3 +436,33 @@ def test_speculative_multi_member_gzip_equals_sequential_decode(tmp_path):
     r = run(bytes(bad))
     assert r["failed"] == 1 and r["fallback"] == 1
     assert run(multi + b"\0" * 100) == dict(size=len(raw), failed=0, fallback=0, multi=1)
+
+
+def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
+    """tgsfilter_b200/csrc/gzenc_core.h (code lengths, canonical codes, dynamic block header — the serial half
+    of the GPU deflate encoder) built for the host: members assembled from it must inflate with zlib to the
+    records; length limiting must keep the codes complete."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "gzenc_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "gzenc_check.cpp"), "-lz", "-o", exe],
+                   check=True)
+    assert subprocess.run([exe, "--selftest"], capture_output=True).returncode == 0
+    rng = np.random.default_rng(5)
+    fib = [1, 1]
+    while len(fib) < 24:
+        fib.append(fib[-1] + fib[-2])
+    q = rng.permutation(np.frombuffer(b"".join(bytes([40 + i]) * c for i, c in enumerate(fib)), dtype=np.uint8)).tobytes()
+    recs = [b"@fib skewed qualities\n" + rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), len(q)).tobytes() + b"\n+\n" + q + b"\n",
+            b"@a\nA\n+\nI\n", b"@homo\n" + b"T" * 5000 + b"\n+\n" + b"#" * 5000 + b"\n",
+            b"@" + b"n" * 300 + b"\nACGTNacgtn\n+\n!~!~!~!~!~\n",
+            b"@wide\n" + rng.choice(np.frombuffer(b"ACGTNRYKM", dtype=np.uint8), 20000).tobytes() + b"\n+\n" +
+            rng.integers(33, 127, 20000).astype(np.uint8).tobytes() + b"\n"]
+    odd = str(tmp_path / "odd.fq")
+    open(odd, "wb").write(b"".join(recs))
+    ont = str(tmp_path / "ont.fq")
+    open(ont, "wb").write(synth.make_config(2, 60, with_names=False).to_fastq())
+    for path in (odd, ont):
+        for fasta in ("0", "1"):
+            r = subprocess.run([exe, path, fasta], capture_output=True, text=True)
+            assert r.returncode == 0 and "roundtrip ok" in r.stdout, (path, fasta, r.stdout, r.stderr)
