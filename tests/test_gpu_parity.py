@@ -725,15 +725,21 @@ def test_gpu_deflate_blocks_odd_records():
             bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 70001))]
     quals = [b"#" * 3000, bytes(rng.integers(33, 127, 4000).astype(np.uint8)), bytes(rng.integers(33, 127, 5000).astype(np.uint8)),
              bytes(rng.integers(33, 60, 70001).astype(np.uint8))]
+    fib = [1, 1]
+    while len(fib) < 24:
+        fib.append(fib[-1] + fib[-2])
+    qf = rng.permutation(np.frombuffer(b"".join(bytes([40 + i]) * c for i, c in enumerate(fib)), dtype=np.uint8)).tobytes()
+    seqs.append(bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), len(qf))))  # forces the 15-bit length limit
+    quals.append(qf)
     import gzip
     for with_q in (True, False):
         batch = synth.pack_reads(seqs, quals if with_q else None)
-        params = FilterParams(min_len=100, min_q=0.0, qtype=33 if with_q else 0, adapters=[], max_read_len=100000, gz_blocks=True)
+        params = FilterParams(min_len=100, min_q=0.0, qtype=33 if with_q else 0, adapters=[], max_read_len=200000, gz_blocks=True)
         with FilterEngine(params) as eng:
             eng.submit(batch)
             blob, spans = eng.collect_gz()
             reads, pieces = eng.collect()
         members, texts = _gz_members(batch, pieces, blob, spans, fastq=with_q)
-        assert len(members) == 4
+        assert len(members) == 5
         for m, t in zip(members, texts):
             assert gzip.decompress(m) == t
