@@ -360,22 +360,6 @@ string new_seq_name(const string &raw, int number) { // newSeqName, T.cpp:1680-1
     return out;
 }
 
-// one gzip member per record, like DeflateCompress (T.cpp:786-812): decompresses identically
-bool gz_member(const string &in, int level, string &out) {
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) return false;
-    out.resize(deflateBound(&zs, in.size()) + 32);
-    zs.next_in = (Bytef *)in.data();
-    zs.avail_in = (uInt)in.size();
-    zs.next_out = (Bytef *)&out[0];
-    zs.avail_out = (uInt)out.size();
-    int rc = deflate(&zs, Z_FINISH);
-    out.resize(zs.total_out);
-    deflateEnd(&zs);
-    return rc == Z_STREAM_END;
-}
-
 const char *kLib[TGSF_LIB_ADAPTERS] = { // adapterLib, T.cpp:2969-2991
     "ATCTCTCTCTTTTCCTCCTCCTCCGTTGTTGTTGTTGAGAGAGAT", "ATCTCTCTCAACAACAACAACGGAGGAGGAGGAAAAGAGAGAGAT",
     "AAAAAAAAAAAAAAAAAATTAACGGAGGAGGAGGA", "TCCTCCTCCTCCGTTAATTTTTTTTTTTTTTTTTT",
@@ -1188,10 +1172,59 @@ int main(int argc, char **argv) {
             fout = fopen(P.OutFile.c_str(), "wb");
             if (!fout) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
         }
-        string gz;
+        // .gz: one member per record, compressed in chunks of ~64 MB by -t threads (same strategy rule as the main pass)
+        std::vector<string> gz_pend;
+        size_t gz_pend_bytes = 0;
+        int gz_strategy = -1;
+        auto deflate_one = [&](z_stream &zs, const string &r, string &dst) {
+            deflateReset(&zs);
+            const size_t at = dst.size(), bound = deflateBound(&zs, r.size()) + 32;
+            dst.resize(at + bound);
+            zs.next_in = (Bytef *)r.data();
+            zs.avail_in = (uInt)r.size();
+            zs.next_out = (Bytef *)&dst[at];
+            zs.avail_out = (uInt)bound;
+            deflate(&zs, Z_FINISH);
+            dst.resize(at + zs.total_out);
+        };
+        auto flush_gz = [&]() {
+            if (gz_pend.empty()) return;
+            if (gz_strategy < 0) { // 16 evenly spaced records, both strategies
+                uint64_t sd = 0, sr = 0;
+                const size_t ns = std::min<size_t>(16, gz_pend.size());
+                for (int which = 0; which < 2; ++which) {
+                    z_stream zs;
+                    memset(&zs, 0, sizeof(zs));
+                    if (deflateInit2(&zs, P.compLevel, Z_DEFLATED, 15 + 16, 8, which ? Z_RLE : Z_DEFAULT_STRATEGY) != Z_OK) continue;
+                    string tmp;
+                    for (size_t a = 0; a < ns; ++a) { tmp.clear(); deflate_one(zs, gz_pend[a * gz_pend.size() / ns], tmp); (which ? sr : sd) += tmp.size(); }
+                    deflateEnd(&zs);
+                }
+                gz_strategy = (!getenv("TGSF_GZ_DEFAULT_STRATEGY") && sr * 100 <= sd * 101) ? Z_RLE : Z_DEFAULT_STRATEGY;
+            }
+            const int K = std::max(1, std::min(P.n_thread, (int)std::thread::hardware_concurrency()));
+            std::vector<string> bufs((size_t)K);
+            auto work = [&](int k) {
+                z_stream zs;
+                memset(&zs, 0, sizeof(zs));
+                if (deflateInit2(&zs, P.compLevel, Z_DEFLATED, 15 + 16, 8, gz_strategy) != Z_OK) return;
+                for (size_t i = gz_pend.size() * (size_t)k / (size_t)K; i < gz_pend.size() * (size_t)(k + 1) / (size_t)K; ++i)
+                    deflate_one(zs, gz_pend[i], bufs[(size_t)k]);
+                deflateEnd(&zs);
+            };
+            std::vector<std::thread> th;
+            for (int k = 1; k < K; ++k) th.emplace_back(work, k);
+            work(0);
+            for (auto &t : th) t.join();
+            for (const string &d : bufs) fwrite(d.data(), 1, d.size(), fout);
+            gz_pend.clear();
+            gz_pend_bytes = 0;
+        };
         auto emit = [&](const char *data, size_t n) {
             if (P.OUTGZ) {
-                if (gz_member(string(data, n), P.compLevel, gz)) fwrite(gz.data(), 1, gz.size(), fout);
+                gz_pend.emplace_back(data, n);
+                gz_pend_bytes += n;
+                if (gz_pend_bytes >= (64u << 20)) flush_gz();
             } else {
                 fwrite(data, 1, n, fout);
             }
@@ -1254,6 +1287,7 @@ int main(int argc, char **argv) {
         qb.release();
         tgsf_destroy(qctx);
         if (!P.Filter) cerr << "INFO: " << downInNum << " reads with a total of " << downInBases << " bases were input." << endl;
+        flush_gz();
         if (fout != stdout) fclose(fout);
         cerr << "INFO: " << S.downNum << " reads with a total of " << S.downBases << " bases after downsampling." << endl;
         if (!P.OutFile.empty()) cerr << "INFO: Downsampled reads were written to: " << P.OutFile << "." << endl;

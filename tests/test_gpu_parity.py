@@ -743,3 +743,17 @@ def test_gpu_deflate_blocks_odd_records():
         assert len(members) == 5
         for m, t in zip(members, texts):
             assert gzip.decompress(m) == t
+
+
+@pytest.mark.parametrize("args", [["-x", "hifi", "-g", "200k", "-d", "3"], ["-x", "hifi", "-F", "-r", "60"]])
+def test_host_cli_downsampled_gzip_output_equals_plain(args):
+    """Downsampling with a .gz output name: per-record members compressed by the -t threads in chunks; the
+    decompressed file must equal the plain output."""
+    import gzip
+    batch = _distinct_length_batch(5, 260)
+    fq = batch.to_fastq()
+    rc1, plain, err1 = _run_host_cli(args, fq)
+    rc2, gz, err2 = _run_host_cli(args, fq, out_name="out.fq.gz")
+    assert rc1 == 0 and rc2 == 0, (err1, err2)
+    assert len(plain) > 10000 and gzip.decompress(gz) == plain
+    assert gz.count(b"\x1f\x8b\x08") >= plain.count(b"\n") // 4
