@@ -31,6 +31,7 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <sys/uio.h>
 #include <unistd.h>
@@ -713,7 +714,7 @@ int main(int argc, char **argv) {
         out = fopen(tmpPath.c_str(), "wb");
         if (!out) { cerr << "Error: Failed to open file: " << tmpPath << endl; return 1; }
     } else if (!P.OnlyQC && !P.OutFile.empty()) {
-        out = fopen(P.OutFile.c_str(), "wb");
+        out = fopen(P.OutFile.c_str(), "w+b"); // read-write: the plain writer maps the file
         if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
     }
     const bool gz_now = P.OUTGZ && !P.Downsample; // T.cpp:2022
@@ -780,6 +781,7 @@ int main(int argc, char **argv) {
     // positioned parallel writes only into a file this process created (stdout may be in append mode)
     const bool out_regular = out != stdout && fstat(out_fd, &out_st) == 0 && S_ISREG(out_st.st_mode) && !getenv("TGSF_SERIAL_WRITER");
     uint64_t out_off = 0; // regular file: bytes written so far
+    bool out_mmap = !getenv("TGSF_NO_MMAP_OUT");
     std::thread writer([&]() {
         string obuf, rec, gz;
         std::vector<Emit> emits;
@@ -1015,11 +1017,51 @@ int main(int argc, char **argv) {
                         }
                         flush();
                     };
-                    std::vector<std::thread> th;
-                    for (int k = 1; k < K; ++k) th.emplace_back(write_range, k);
-                    write_range(0);
-                    for (auto &t : th) t.join();
-                    out_off += bytes_before[(size_t)K];
+                    // A regular file takes its inode lock for every buffered write, so positioned writes from
+                    // several threads serialise.  Preferred path: reserve the batch's byte range (fallocate, so a
+                    // full disk is an error here and not a SIGBUS later), map it and let the threads copy their
+                    // records into the mapping; the pwritev path stays as the fallback (pipes, odd filesystems).
+                    bool mapped = false;
+                    const uint64_t nbytes = bytes_before[(size_t)K];
+                    if (out_regular && out_mmap && nbytes) {
+                        const uint64_t page = (uint64_t)sysconf(_SC_PAGESIZE);
+                        const uint64_t map_off = out_off & ~(page - 1), delta = out_off - map_off;
+                        if (fallocate(out_fd, 0, (off_t)out_off, (off_t)nbytes) == 0) {
+                            void *m = mmap(nullptr, (size_t)(nbytes + delta), PROT_READ | PROT_WRITE, MAP_SHARED, out_fd, (off_t)map_off);
+                            if (m != MAP_FAILED) {
+                                auto copy_range = [&](int k) {
+                                    char *dst = (char *)m + delta + bytes_before[(size_t)k];
+                                    for (size_t i = cut[(size_t)k]; i < cut[(size_t)k + 1]; ++i) {
+                                        const Emit &e = emits[i];
+                                        *dst++ = P.Outfq == 1 ? '@' : '>';
+                                        memcpy(dst, nm[i]->data(), nm[i]->size()); dst += nm[i]->size();
+                                        *dst++ = '\n';
+                                        memcpy(dst, b.bases.data() + b.offsets[e.read] + e.start, e.len); dst += e.len;
+                                        if (P.Outfq == 1) {
+                                            memcpy(dst, kPlus, 3); dst += 3;
+                                            memcpy(dst, b.quals.data() + b.offsets[e.read] + e.start, e.len); dst += e.len;
+                                        }
+                                        *dst++ = '\n';
+                                    }
+                                };
+                                std::vector<std::thread> th;
+                                for (int k = 1; k < K; ++k) th.emplace_back(copy_range, k);
+                                copy_range(0);
+                                for (auto &t : th) t.join();
+                                munmap(m, (size_t)(nbytes + delta));
+                                mapped = true;
+                            }
+                        } else {
+                            out_mmap = false; // filesystem without fallocate: keep to pwritev
+                        }
+                    }
+                    if (!mapped) {
+                        std::vector<std::thread> th;
+                        for (int k = 1; k < K; ++k) th.emplace_back(write_range, k);
+                        write_range(0);
+                        for (auto &t : th) t.join();
+                    }
+                    out_off += nbytes;
                 }
             }
             batch_pool.put(std::move(job->rb));
