@@ -508,8 +508,15 @@ private:
             if (distance > avail || distance > HIST) { fail("invalid match distance"); ret = -1; break; }
             const uint8_t *src = out - distance;
             uint8_t *const stop = out + len;
-            if (distance >= 8) { // word copies; may write up to 7 bytes past stop (SLACK)
-                do { memcpy(out, src, 8); out += 8; src += 8; } while (out < stop);
+            if (distance >= 8) { // word copies; may write up to 15 bytes past stop (SLACK)
+                // short matches dominate FASTQ streams: two unconditional words, a loop only beyond 16 bytes
+                memcpy(out, src, 8);
+                memcpy(out + 8, src + 8, 8);
+                if (len > 16) {
+                    out += 16;
+                    src += 16;
+                    do { memcpy(out, src, 8); out += 8; src += 8; } while (out < stop);
+                }
             } else if (distance == 1) {
                 memset(out, *src, len);
             } else {
