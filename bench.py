@@ -504,6 +504,8 @@ def main():
         class _Blk:  # zero-copy view of the device counter block
             __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
         blk = torch.as_tensor(_Blk(), device=device)
+        warm = torch.zeros(nwords, dtype=torch.int64, device=device)  # same size: NCCL sets its channels up lazily
+        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         a0 = time.perf_counter()
         dist.all_reduce(blk, op=dist.ReduceOp.SUM)
