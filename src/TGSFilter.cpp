@@ -1110,6 +1110,7 @@ int main(int argc, char **argv) {
         job->rb = std::move(sl.rb);
         to_write.push(std::move(job));
     };
+    const int stage_threads = getenv("TGSF_STAGE_THREADS") ? std::max(1, atoi(getenv("TGSF_STAGE_THREADS"))) : 4;
     int cur = 0;
     double t_wait_in = 0, t_pack = 0, t_copy = 0, t_submit = 0, t_retire = 0;
     Timer T_loop;
@@ -1130,18 +1131,51 @@ int main(int argc, char **argv) {
         t_retire += T_loop.lap();
         PinSlot &sl = ring[(size_t)cur];
         if (!sl.reserve((size_t)nb + 64)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
+        // pack the bases (2 bits) and copy the qualities into the pinned slot on a few threads: the ranges are
+        // multiples of 32 bases, their exception lists are concatenated with the range offset added
         uint64_t ne = 0;
-        sl.exc_pos.resize(std::max<size_t>(sl.exc_pos.size(), 1024));
-        sl.exc_byte.resize(sl.exc_pos.size());
-        int rc = tgsf_pack_bases(rb->bases.data(), nb, sl.packed, sl.exc_pos.data(), sl.exc_byte.data(), sl.exc_pos.size(), &ne);
-        if (rc == TGSF_ERR_CAPACITY) {
-            sl.exc_pos.resize(ne);
-            sl.exc_byte.resize(ne);
-            rc = tgsf_pack_bases(rb->bases.data(), nb, sl.packed, sl.exc_pos.data(), sl.exc_byte.data(), sl.exc_pos.size(), &ne);
+        {
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)stage_threads, nb >> 22));
+            const uint64_t chunk = ((nb / (uint64_t)T + 31) / 32) * 32;
+            std::vector<std::vector<uint64_t>> xp((size_t)T);
+            std::vector<std::vector<uint8_t>> xb((size_t)T);
+            std::vector<int> rcs((size_t)T, TGSF_OK);
+            auto stage = [&](int t) {
+                const uint64_t lo = std::min<uint64_t>(nb, (uint64_t)t * chunk), hi = t == T - 1 ? nb : std::min<uint64_t>(nb, lo + chunk);
+                if (hi > lo) {
+                    uint64_t k = 0;
+                    xp[(size_t)t].resize(1024);
+                    xb[(size_t)t].resize(1024);
+                    int r = tgsf_pack_bases(rb->bases.data() + lo, hi - lo, sl.packed + lo / 4, xp[(size_t)t].data(), xb[(size_t)t].data(), 1024, &k);
+                    if (r == TGSF_ERR_CAPACITY) {
+                        xp[(size_t)t].resize((size_t)k);
+                        xb[(size_t)t].resize((size_t)k);
+                        r = tgsf_pack_bases(rb->bases.data() + lo, hi - lo, sl.packed + lo / 4, xp[(size_t)t].data(), xb[(size_t)t].data(), k, &k);
+                    }
+                    xp[(size_t)t].resize((size_t)k);
+                    xb[(size_t)t].resize((size_t)k);
+                    for (uint64_t &q : xp[(size_t)t]) q += lo;
+                    rcs[(size_t)t] = r;
+                    if (has_qual) memcpy(sl.quals + lo, rb->quals.data() + lo, (size_t)(hi - lo));
+                } else {
+                    xp[(size_t)t].clear();
+                    xb[(size_t)t].clear();
+                }
+            };
+            std::vector<std::thread> th;
+            for (int t = 1; t < T; ++t) th.emplace_back(stage, t);
+            stage(0);
+            for (auto &x : th) x.join();
+            sl.exc_pos.clear();
+            sl.exc_byte.clear();
+            for (int t = 0; t < T; ++t) {
+                if (rcs[(size_t)t] != TGSF_OK) die_tgsf("tgsf_pack_bases");
+                sl.exc_pos.insert(sl.exc_pos.end(), xp[(size_t)t].begin(), xp[(size_t)t].end());
+                sl.exc_byte.insert(sl.exc_byte.end(), xb[(size_t)t].begin(), xb[(size_t)t].end());
+            }
+            ne = sl.exc_pos.size();
         }
-        if (rc != TGSF_OK) die_tgsf("tgsf_pack_bases");
         t_pack += T_loop.lap();
-        if (has_qual && nb) memcpy(sl.quals, rb->quals.data(), nb);
         t_copy += T_loop.lap();
         if (tgsf_submit_packed(ctx[(size_t)(cur % P.gpus)], sl.packed, has_qual ? sl.quals : nullptr, rb->offsets.data(), n,
                                sl.exc_pos.data(), sl.exc_byte.data(), ne) != TGSF_OK)
