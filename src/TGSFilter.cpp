@@ -1111,6 +1111,7 @@ int main(int argc, char **argv) {
         to_write.push(std::move(job));
     };
     const int stage_threads = getenv("TGSF_STAGE_THREADS") ? std::max(1, atoi(getenv("TGSF_STAGE_THREADS"))) : 4;
+    const int stage_shift = getenv("TGSF_STAGE_MIN_SHIFT") ? std::max(6, atoi(getenv("TGSF_STAGE_MIN_SHIFT"))) : 22; // >= 4 Mbases per thread
     int cur = 0;
     double t_wait_in = 0, t_pack = 0, t_copy = 0, t_submit = 0, t_retire = 0;
     Timer T_loop;
@@ -1135,7 +1136,7 @@ int main(int argc, char **argv) {
         // multiples of 32 bases, their exception lists are concatenated with the range offset added
         uint64_t ne = 0;
         {
-            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)stage_threads, nb >> 22));
+            const int T = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)stage_threads, nb >> stage_shift));
             const uint64_t chunk = ((nb / (uint64_t)T + 31) / 32) * 32;
             std::vector<std::vector<uint64_t>> xp((size_t)T);
             std::vector<std::vector<uint8_t>> xb((size_t)T);

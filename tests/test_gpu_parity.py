@@ -757,3 +757,27 @@ def test_host_cli_downsampled_gzip_output_equals_plain(args):
     assert rc1 == 0 and rc2 == 0, (err1, err2)
     assert len(plain) > 10000 and gzip.decompress(gz) == plain
     assert gz.count(b"\x1f\x8b\x08") >= plain.count(b"\n") // 4
+
+
+def test_host_cli_multi_threaded_staging_equals_single(monkeypatch):
+    """The batch staging (2-bit packing + quality copy into the pinned slot) is split over threads at 32-base
+    boundaries; exception bytes (N, lower case) near the cuts must land at the right absolute positions."""
+    rng = np.random.default_rng(21)
+    batch = synth.make_config(2, 300, max_len=30000)
+    fq = bytearray(batch.to_fastq())
+    # sprinkle N / lower-case bases over the sequence lines
+    lines = bytes(fq).split(b"\n")
+    for i in range(1, len(lines), 4):
+        ln = bytearray(lines[i])
+        for p in rng.integers(0, len(ln), max(1, len(ln) // 40)):
+            ln[int(p)] = b"Nacgtn"[int(rng.integers(0, 6))]
+        lines[i] = bytes(ln)
+    fq = b"\n".join(lines)
+    monkeypatch.setenv("TGSF_STAGE_THREADS", "1")
+    rc1, out1, err1 = _run_host_cli(["-x", "ont"], fq)
+    monkeypatch.setenv("TGSF_STAGE_THREADS", "7")
+    monkeypatch.setenv("TGSF_STAGE_MIN_SHIFT", "12")
+    rc2, out2, err2 = _run_host_cli(["-x", "ont"], fq)
+    assert rc1 == 0 and rc2 == 0, (err1, err2)
+    assert out1 == out2 and len(out1) > 100000
+    assert _info(err1) == _info(err2)

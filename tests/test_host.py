@@ -466,3 +466,39 @@ def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
         for fasta in ("0", "1"):
             r = subprocess.run([exe, path, fasta], capture_output=True, text=True)
             assert r.returncode == 0 and "roundtrip ok" in r.stdout, (path, fasta, r.stdout, r.stderr)
+
+
+def test_pack_bases_in_ranges_equals_one_call():
+    """The C++ host packs a batch on several threads: ranges cut at multiples of 32 bases, each packed into
+    packed + lo / 4, exception positions shifted by lo (src/TGSFilter.cpp).  Same bytes as one call."""
+    lib = _capi.load()
+    rng = np.random.default_rng(11)
+    for n, threads in ((100_003, 4), (1 << 16, 7), (999, 3), (64, 2)):
+        b = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, n)].copy()
+        hits = rng.integers(0, n, max(3, n // 50))
+        b[hits] = np.frombuffer(b"Nacgtn", dtype=np.uint8)[rng.integers(0, 6, len(hits))]
+        cap = n + 8
+
+        def pack(lo, hi, packed):
+            pos = np.zeros(cap, dtype=np.uint64)
+            val = np.zeros(cap, dtype=np.uint8)
+            ne = C.c_uint64(0)
+            rc = lib.tgsf_pack_bases(b.ctypes.data + lo, hi - lo, packed.ctypes.data + lo // 4, pos.ctypes.data,
+                                     val.ctypes.data, cap, C.byref(ne))
+            assert rc == 0
+            return pos[:ne.value] + lo, val[:ne.value]
+
+        whole = np.zeros(n // 4 + 64, dtype=np.uint8)
+        wp, wv = pack(0, n, whole)
+        parts = np.zeros(n // 4 + 64, dtype=np.uint8)
+        chunk = ((n // threads + 31) // 32) * 32
+        pp, pv = [], []
+        for t in range(threads):
+            lo = min(n, t * chunk)
+            hi = n if t == threads - 1 else min(n, lo + chunk)
+            if hi > lo:
+                p_, v_ = pack(lo, hi, parts)
+                pp.append(p_)
+                pv.append(v_)
+        assert np.array_equal(whole, parts)
+        assert np.array_equal(wp, np.concatenate(pp)) and np.array_equal(wv, np.concatenate(pv))
