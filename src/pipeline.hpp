@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "inflate.hpp"
+#include "pinflate.hpp"
 
 namespace ingest {
 
@@ -78,6 +79,10 @@ public:
         } else if (gz && !getenv("TGSF_ZLIB_INFLATE") && inflate_threads() > 1 && fastgz::MultiMemberReader::is_multi_member(path)) {
             mm_.reset(new fastgz::MultiMemberReader(path, inflate_threads())); // concatenated members, speculative spans
             if (!mm_->ok()) mm_.reset();
+        } else if (gz && !getenv("TGSF_ZLIB_INFLATE") && !getenv("TGSF_SERIAL_INFLATE") && inflate_threads() > 1 &&
+                   fastgz::SingleStreamReader::worthwhile(path)) {
+            ss_.reset(new fastgz::SingleStreamReader(path, inflate_threads())); // one deflate stream, two-pass parallel decode
+            if (!ss_->ok()) ss_.reset();
         } else if (gz && !getenv("TGSF_ZLIB_INFLATE")) {
             gz_.reset(new fastgz::GzReader(path)); // own inflate (src/inflate.hpp); zlib kept for A/B runs
             if (!gz_->ok()) gz_.reset();
@@ -115,7 +120,7 @@ public:
         if (f_) gzclose(f_);
         if (fd_ >= 0) close(fd_);
     }
-    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr || bgzf_ != nullptr || mm_ != nullptr; }
+    bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr || bgzf_ != nullptr || mm_ != nullptr || ss_ != nullptr; }
     static int inflate_threads() { // TGSF_INFLATE_THREADS, default min(8, cores - 2)
         if (const char *e = getenv("TGSF_INFLATE_THREADS")) return std::max(1, atoi(e));
         return std::max(1, std::min(8, (int)std::thread::hardware_concurrency() - 2));
@@ -204,11 +209,13 @@ private:
         if (len_ == buf_.size()) buf_.resize(buf_.size() * 2); // one record larger than the buffer
         while (len_ < buf_.size()) {
             const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
-            const long got = mm_ ? (long)mm_->read(buf_.data() + len_, want)
+            const long got = ss_ ? (long)ss_->read(buf_.data() + len_, want)
+                           : mm_ ? (long)mm_->read(buf_.data() + len_, want)
                            : bgzf_ ? (long)bgzf_->read(buf_.data() + len_, want)
                            : gz_ ? (long)read_inflated(buf_.data() + len_, want)
                            : f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want)
                                 : (long)read(fd_, buf_.data() + len_, want);
+            if (ss_ && got == 0 && ss_->failed()) std::cerr << "Error: " << ss_->error() << " (gzip input)" << std::endl;
             if (mm_ && got == 0 && mm_->failed()) std::cerr << "Error: " << mm_->error() << " (gzip input)" << std::endl;
             if (bgzf_ && got == 0 && bgzf_->failed()) std::cerr << "Error: " << bgzf_->error() << " (BGZF input)" << std::endl;
             if (gz_ && got == 0 && gz_->failed()) std::cerr << "Error: " << gz_->error() << " (gzip input)" << std::endl;
@@ -241,6 +248,7 @@ private:
     std::unique_ptr<fastgz::GzReader> gz_;
     std::unique_ptr<fastgz::BgzfParallelReader> bgzf_;
     std::unique_ptr<fastgz::MultiMemberReader> mm_;
+    std::unique_ptr<fastgz::SingleStreamReader> ss_;
     std::thread inflater_;
     std::atomic<bool> stop_inflater_{false};
     Queue<std::unique_ptr<std::vector<char>>> chunks_{4};

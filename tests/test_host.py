@@ -438,6 +438,87 @@ def test_speculative_multi_member_gzip_equals_sequential_decode(tmp_path):
     assert run(multi + b"\0" * 100) == dict(size=len(raw), failed=0, fallback=0, multi=1)
 
 
+def test_parallel_single_stream_inflate_equals_sequential_decode(tmp_path):
+    """fastgz::SingleStreamReader (src/pinflate.hpp; one-member .fastq.gz as written by gzip or pigz): spans
+    start at block boundaries found by search and are decoded against an unknown 32 KB window, then accepted
+    only as an unbroken chain from the member's first block.  Every zlib level and strategy, streams with
+    sync/full flushes (pigz's chunking), stored-only and fixed-only streams, binary and mixed data (search
+    finds nothing: spans are decoded again from the proven boundary), trailing members, corrupt bytes,
+    truncation and a damaged trailer must give exactly the sequential decoder's bytes and verdict."""
+    import gzip
+    import io
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "pinflate_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "pinflate_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(5)
+    recs = []
+    for i in range(220):
+        ln = int(rng.integers(100, 30000))
+        recs.append(b"@r%d\n" % i + rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), ln).tobytes() + b"\n+\n" +
+                    rng.integers(33, 75, ln).astype(np.uint8).tobytes() + b"\n")
+    fq = b"".join(recs)  # ~6.5 MB -> ~3.5 MB compressed: ~50 spans of 64 KB
+    datasets = {
+        "fastq": fq,
+        "random": rng.integers(0, 256, 700_000, dtype=np.uint8).tobytes(),
+        "runs": (b"A" * 100000 + b"CG" * 50000 + b"ACGTACG" * 30000 + bytes(rng.integers(65, 70, 1000, dtype=np.uint8))) * 3,
+        "mixed": fq[:1_500_000] + rng.integers(0, 256, 200_000, dtype=np.uint8).tobytes() + fq[1_500_000:3_000_000],
+        "empty": b"",
+        "one": b"x",
+    }
+
+    def comp(data, level, strategy=zlib.Z_DEFAULT_STRATEGY):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31, 8, strategy)
+        return c.compress(data) + c.flush()
+
+    def flushed(data, kind):
+        c = zlib.compressobj(6, zlib.DEFLATED, 31)
+        out = b"".join(c.compress(data[i:i + 131072]) + c.flush(kind) for i in range(0, len(data), 131072))
+        return out + c.flush()
+
+    path = str(tmp_path / "t.gz")
+
+    def run(blob, what, threads=("1", "5"), span="65536", rs="1048576", failed=0):
+        with open(path, "wb") as f:
+            f.write(blob)
+        res = None
+        for t in threads:
+            r = subprocess.run([exe, path, t, span, rs], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, (what, t, r.stdout, r.stderr)
+            w = r.stdout.split()
+            assert (int(w[3]), int(w[4])) == (failed, failed), (what, t, r.stdout)
+            res = dict(size=int(w[1]), spans=int(w[-3]), repairs=int(w[-1]))
+        return res
+
+    for name, d in datasets.items():
+        variants = [("l%d" % lv, comp(d, lv)) for lv in (0, 1, 6, 9)]
+        variants += [("fixed", comp(d, 6, zlib.Z_FIXED)), ("huff", comp(d, 6, zlib.Z_HUFFMAN_ONLY)),
+                     ("sync", flushed(d, zlib.Z_SYNC_FLUSH)), ("full", flushed(d, zlib.Z_FULL_FLUSH))]
+        bio = io.BytesIO()
+        for part in (d[:len(d) // 2], b"", d[len(d) // 2:]):
+            with gzip.GzipFile(filename="some_name.fq", mode="wb", fileobj=bio, compresslevel=5) as g:
+                g.write(part)
+        variants.append(("multi", bio.getvalue() + b"\0\0\0\0"))
+        for vn, z in variants:
+            r = run(z, (name, vn))
+            assert r["size"] == len(d)
+            if name == "fastq" and vn in ("l1", "l6", "l9", "huff", "sync", "full"):
+                # text in dynamic blocks: the search lines the spans up (a flush's empty stored block is decoded through)
+                assert r["spans"] > 20 and r["repairs"] <= r["spans"] // 10, (vn, r)
+    z = bytearray(comp(fq[:3_000_000], 6))
+    for pos in (50, 1000, len(z) // 2, len(z) - 200, len(z) - 9, len(z) - 5):  # the last two: CRC-32, ISIZE
+        zz = bytearray(z)
+        zz[pos] ^= 0x55
+        run(bytes(zz), ("corrupt", pos), failed=1)
+    run(bytes(z[:len(z) // 2]), "truncated", failed=1)
+    run(bytes(z[:len(z) - 4]), "truncated trailer", failed=1)
+    run(bytes(z), "odd read size", threads=("4",), rs="4099")
+    run(bytes(z), "default and oversized span", threads=("4",), span="0")
+    run(bytes(z), "default and oversized span", threads=("4",), span="16777216")
+
+
 def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
     """tgsfilter_b200/csrc/gzenc_core.h (code lengths, canonical codes, dynamic block header — the serial half
     of the GPU deflate encoder) built for the host: members assembled from it must inflate with zlib to the
