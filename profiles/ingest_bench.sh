@@ -14,3 +14,6 @@ echo -n "gzip 16 members, own inflate, 1 thr:  "; TGSF_INFLATE_THREADS=1 INGEST_
 echo -n "gzip 16 members, zlib:                "; TGSF_ZLIB_INFLATE=1 INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in16.fq.gz 1 67108864 1
 for n in 1 2 4 8; do echo -n "gzip 16 members, $n inflate threads:   "; TGSF_INFLATE_THREADS=$n INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in16.fq.gz 1 67108864 1; done
 for n in 1 2 4 8; do echo -n "BGZF, $n inflate threads:              "; TGSF_INFLATE_THREADS=$n INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in.fq.gz 1 67108864 1; done
+# one deflate stream (plain `gzip`): two-pass parallel decode, src/pinflate.hpp
+zcat /dev/shm/f2f/in16.fq.gz | gzip -1 > /dev/shm/f2f/in1.fq.gz
+for n in 1 2 4 8; do echo -n "gzip single member, $n inflate threads: "; TGSF_INFLATE_THREADS=$n INGEST_ONLY=serial t /tmp/ingest_check /dev/shm/f2f/in1.fq.gz 1 67108864 1; done

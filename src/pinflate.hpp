@@ -17,7 +17,8 @@
 //      from the known boundary.  With the previous span's last 32 KB resolved, the placeholders are
 //      replaced through a 33 K-entry lookup table and the span's CRC-32 is taken, both on the workers;
 //      the consumer combines the CRCs (crc32_combine) and checks the member trailer.
-// Bytes after the member (further members, padding) go to the streaming GzReader.
+// A large member behind this one (`cat a.fq.gz b.fq.gz`) gets a reader of its own; small remainders and
+// padding go to the streaming GzReader.
 // tests/cpp/pinflate_check.cpp pins it against the sequential GzReader and zlib.
 #pragma once
 #include "inflate.hpp"
@@ -414,34 +415,23 @@ public:
             if (m == MAP_FAILED) return;
             base_ = (const uint8_t *)m;
         }
-        data0_ = size_ ? pinf::gzip_header_len(base_, size_) : 0;
-        if (!data0_) { // not a gzip member: let the streaming reader report it
-            tail_.reset(new GzReader(base_, size_));
-            ok_ = true;
-            return;
-        }
-        threads = std::max(1, threads);
-        span_ = span_bytes ? span_bytes : std::min<size_t>(2u << 20, std::max<size_t>(256u << 10, (size_ - data0_) / (4 * (size_t)threads)));
-        nspans_ = (size_ - data0_ + span_ - 1) / span_;
-        found_.reset(new std::atomic<uint64_t>[nspans_ + 1]);
-        for (size_t i = 0; i <= nspans_; ++i) found_[i].store(UNKNOWN);
-        window_ = (size_t)threads + 3;
-        chain_end_bit_ = 8ull * data0_;
-        chain_window_.assign(pinf::HIST, 0);
-        ok_ = true;
-        for (int t = 0; t < threads; ++t) workers_.emplace_back([this] { work(); });
+        start(threads, span_bytes);
+    }
+    // a member inside a mapped file (the members after the first one of a `cat`-ed file)
+    SingleStreamReader(const uint8_t *data, size_t n, int threads, size_t span_bytes) : base_(data), size_(n), borrowed_(true) {
+        start(threads, span_bytes);
     }
     ~SingleStreamReader() {
         shutdown();
         for (auto &p : sym_pool_) delete[] p.first;
-        if (base_) munmap((void *)base_, size_);
+        if (base_ && !borrowed_) munmap((void *)base_, size_);
         if (fd_ >= 0) close(fd_);
     }
     bool ok() const { return ok_; }
     bool failed() const { return error_ != nullptr; }
     const char *error() const { return error_; }
-    size_t repairs() const { return repairs_; } // spans decoded a second time (tests, diagnostics)
-    size_t spans() const { return nspans_; }
+    size_t repairs() const { return repairs_ + (next_ ? next_->repairs() : 0); } // spans decoded a second time (tests, diagnostics)
+    size_t spans() const { return nspans_ + (next_ ? next_->spans() : 0); }
     // worker seconds spent in block search / symbolic decode / placeholder resolution + CRC (diagnostics)
     void phase_seconds(double out[3]) const { for (int i = 0; i < 3; ++i) out[i] = phase_ns_[i].load() * 1e-9; }
 
@@ -449,6 +439,12 @@ public:
         uint8_t *d = (uint8_t *)dst;
         size_t got = 0;
         while (got < n && !error_) {
+            if (next_) {
+                const size_t k = next_->read(d + got, n - got);
+                if (k == 0) { if (next_->failed()) error_ = next_->error(); break; }
+                got += k;
+                continue;
+            }
             if (tail_) {
                 const size_t k = tail_->read(d + got, n - got);
                 if (k == 0) { if (tail_->failed()) error_ = tail_->error(); break; }
@@ -504,6 +500,25 @@ private:
         ~Task() { delete[] sym; }
     };
 
+    void start(int threads, size_t span_bytes) {
+        threads_ = std::max(1, threads);
+        span_arg_ = span_bytes;
+        data0_ = size_ ? pinf::gzip_header_len(base_, size_) : 0;
+        ok_ = true;
+        if (!data0_) { // empty or not a gzip member: the streaming reader reports it
+            tail_.reset(new GzReader(base_, size_));
+            return;
+        }
+        span_ = span_bytes ? span_bytes : std::min<size_t>(2u << 20, std::max<size_t>(256u << 10, (size_ - data0_) / (4 * (size_t)threads_)));
+        nspans_ = (size_ - data0_ + span_ - 1) / span_;
+        found_.reset(new std::atomic<uint64_t>[nspans_ + 1]);
+        for (size_t i = 0; i <= nspans_; ++i) found_[i].store(UNKNOWN);
+        window_ = (size_t)threads_ + 3;
+        chain_end_bit_ = 8ull * data0_;
+        chain_window_.assign(pinf::HIST, 0);
+        for (int t = 0; t < threads_; ++t) workers_.emplace_back([this] { work(); });
+    }
+
     void shutdown() {
         {
             std::lock_guard<std::mutex> lk(m_);
@@ -527,8 +542,11 @@ private:
         off += 8;
         if (crc != crc_) { error_ = "gzip CRC mismatch"; return; }
         if (isize != (uint32_t)total_) { error_ = "gzip length mismatch"; return; }
-        if (off < size_) tail_.reset(new GzReader(base_ + off, size_ - off));
-        else finished_ = true;
+        while (off < size_ && base_[off] == 0) ++off; // zero padding between / after members
+        if (off >= size_) finished_ = true;
+        else if (size_ - off >= (1u << 20) && pinf::gzip_header_len(base_ + off, size_ - off))
+            next_.reset(new SingleStreamReader(base_ + off, size_ - off, threads_, span_arg_)); // a large member follows
+        else tail_.reset(new GzReader(base_ + off, size_ - off));
     }
 
     // ---- symbol buffers are recycled: a span's buffer is tens of MB and fresh pages are slow ----
@@ -790,6 +808,10 @@ private:
     std::deque<std::unique_ptr<Task>> tasks_;
     std::vector<std::thread> workers_;
     std::unique_ptr<GzReader> tail_;
+    std::unique_ptr<SingleStreamReader> next_;
+    int threads_ = 1;
+    size_t span_arg_ = 0;
+    bool borrowed_ = false;
     std::mutex m_, pool_m_;
     std::condition_variable cv_;
     std::vector<std::pair<uint16_t *, size_t>> sym_pool_;
