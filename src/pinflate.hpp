@@ -399,10 +399,12 @@ inline size_t gzip_header_len(const uint8_t *p, size_t n) {
 
 class SingleStreamReader {
 public:
-    // worth it: a file of at least a few spans
+    // worth it: a file of at least a few spans (TGSF_PINFLATE_MIN_BYTES: tests)
     static bool worthwhile(const std::string &path) {
         struct stat st;
-        return stat(path.c_str(), &st) == 0 && (size_t)st.st_size >= (4u << 20);
+        const char *e = getenv("TGSF_PINFLATE_MIN_BYTES");
+        const size_t min_bytes = e ? (size_t)strtoull(e, nullptr, 10) : (size_t)(4u << 20);
+        return stat(path.c_str(), &st) == 0 && (size_t)st.st_size >= min_bytes;
     }
 
     SingleStreamReader(const std::string &path, int threads, size_t span_bytes = 0) {
@@ -509,7 +511,7 @@ private:
             tail_.reset(new GzReader(base_, size_));
             return;
         }
-        span_ = span_bytes ? span_bytes : std::min<size_t>(2u << 20, std::max<size_t>(256u << 10, (size_ - data0_) / (4 * (size_t)threads_)));
+        span_ = span_bytes ? span_bytes : std::min<size_t>(2u << 20, std::max<size_t>(128u << 10, (size_ - data0_) / (4 * (size_t)threads_)));
         nspans_ = (size_ - data0_ + span_ - 1) / span_;
         found_.reset(new std::atomic<uint64_t>[nspans_ + 1]);
         for (size_t i = 0; i <= nspans_; ++i) found_[i].store(UNKNOWN);

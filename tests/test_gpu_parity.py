@@ -781,3 +781,23 @@ def test_host_cli_multi_threaded_staging_equals_single(monkeypatch):
     assert rc1 == 0 and rc2 == 0, (err1, err2)
     assert out1 == out2 and len(out1) > 100000
     assert _info(err1) == _info(err2)
+
+
+def test_host_cli_parallel_single_stream_gzip_input(monkeypatch):
+    """A one-member .fastq.gz goes through src/pinflate.hpp (spans decoded in parallel against an unknown
+    window, chain-validated): records and INFO lines must equal those of the plain input and of the
+    sequential decoder (TGSF_SERIAL_INFLATE=1)."""
+    import gzip
+    batch = synth.make_config(2, 300, max_len=30000)
+    fq = batch.to_fastq()
+    gz = gzip.compress(fq, 6)
+    assert len(gz) > 1_000_000
+    rc0, out0, err0 = _run_host_cli(["-x", "ont"], fq)
+    monkeypatch.setenv("TGSF_PINFLATE_MIN_BYTES", "100000")
+    monkeypatch.setenv("TGSF_INFLATE_THREADS", "6")
+    rc1, out1, err1 = _run_host_cli(["-x", "ont"], gz, in_name="in.fq.gz")
+    monkeypatch.setenv("TGSF_SERIAL_INFLATE", "1")
+    rc2, out2, err2 = _run_host_cli(["-x", "ont"], gz, in_name="in.fq.gz")
+    assert rc0 == 0 and rc1 == 0 and rc2 == 0, (err0, err1, err2)
+    assert out1 == out0 and out2 == out0 and len(out0) > 100000
+    assert _info(err1) == _info(err0) and _info(err2) == _info(err0)
