@@ -305,9 +305,9 @@ public:
                     src += 16;
                     do { memcpy(out, src, 16); out += 8; src += 8; } while (out < stop);
                 }
-            } else if (distance == 1) {
-                const uint16_t v = *src;
-                do { *out++ = v; } while (out < stop);
+            } else if (distance == 1) { // a run: 8 symbols per step, up to 7 past stop
+                const uint64_t v4 = (uint64_t)*src * 0x0001000100010001ull;
+                do { memcpy(out, &v4, 8); memcpy(out + 4, &v4, 8); out += 8; } while (out < stop);
             } else {
                 do { *out++ = *src++; } while (out < stop);
             }
@@ -512,7 +512,8 @@ private:
             return;
         }
         span_ = span_bytes ? span_bytes : std::min<size_t>(2u << 20, std::max<size_t>(128u << 10, (size_ - data0_) / (4 * (size_t)threads_)));
-        nspans_ = (size_ - data0_ + span_ - 1) / span_;
+        nspans_ = nspans0_ = (size_ - data0_ + span_ - 1) / span_;
+        if (const char *e = getenv("TGSF_PINFLATE_SOFT_CAP")) soft_cap_ = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10)); // tests
         found_.reset(new std::atomic<uint64_t>[nspans_ + 1]);
         for (size_t i = 0; i <= nspans_; ++i) found_[i].store(UNKNOWN);
         window_ = (size_t)threads_ + 3;
@@ -624,10 +625,13 @@ private:
                 // Stop where the next span starts.  A boundary in front of that start is a block the search
                 // did not accept (stored or fixed block — every pigz / Z_SYNC_FLUSH chunk ends with one —,
                 // non-text literals): keep decoding, so that such blocks cost no second decode.
-                if (!speculate_.load(std::memory_order_relaxed) || t.idx + 1 >= nspans_) break;
+                if (!speculate_.load(std::memory_order_relaxed) || t.idx + 1 >= nspans0_) break;
                 const uint64_t next = span_start(t.idx + 1, D);
                 if (next >= NOT_FOUND || pos >= next) break;
             }
+            // Memory bound for streams that expand enormously (a span of 2 MB can hold GBs of runs): close the
+            // span at this boundary; the spans behind it no longer line up and are decoded from here in turn.
+            if ((size_t)(out - t.sym) - HIST >= soft_cap_) break;
             if (t.cancel.load(std::memory_order_relaxed)) return;
             unsigned type;
             if ((t.err = D.block_header(final, type))) break;
@@ -688,6 +692,10 @@ private:
                 chain_valid_ = std::min<size_t>(HIST, chain_valid_ + t.nsym);
             }
             chain_end_bit_ = t.end_bit;
+            if (!t.final && !t.err && t.idx + 1 >= nspans_) { // the last span was closed early (soft cap): one more
+                ++nspans_;
+                scan_done_ = false;
+            }
             if (t.final || t.err) {
                 chain_closed_ = true;
                 scan_done_ = true;
@@ -747,7 +755,7 @@ private:
         tasks_.emplace_back(new Task());
         Task *t = tasks_.back().get();
         t->idx = next_idx_++;
-        t->stop_bit = t->idx + 1 >= nspans_ ? (uint64_t)-1 : 8ull * (data0_ + (t->idx + 1) * span_);
+        t->stop_bit = t->idx + 1 >= nspans0_ ? (uint64_t)-1 : 8ull * (data0_ + (t->idx + 1) * span_);
         if (t->idx == 0 || known) {
             t->known_start = true;
             t->start_bit = t->idx == 0 ? 8ull * data0_ : chain_end_bit_;
@@ -773,8 +781,9 @@ private:
                             if (p->state == QUEUED) { t = p.get(); break; }
                     if (t) { t->state = resolve ? RESOLVING : DECODING; break; }
                     if (!scan_done_ && tasks_.size() < window_) {
-                        if (speculate_.load() || next_idx_ == 0) { t = new_task(false); break; }
-                        if (chain_next_ == next_idx_) { t = new_task(true); break; } // serial mode: previous span accepted
+                        const bool from_chain = !speculate_.load() || next_idx_ >= nspans0_; // start known only once the chain is there
+                        if (!from_chain || next_idx_ == 0) { t = new_task(false); break; }
+                        if (chain_next_ == next_idx_) { t = new_task(true); break; }
                     }
                     cv_.wait(lk);
                 }
@@ -795,7 +804,8 @@ private:
 
     int fd_ = -1;
     const uint8_t *base_ = nullptr;
-    size_t size_ = 0, data0_ = 0, span_ = 0, nspans_ = 0, window_ = 8;
+    size_t size_ = 0, data0_ = 0, span_ = 0, nspans_ = 0, nspans0_ = 0, window_ = 8;
+    size_t soft_cap_ = 96u << 20; // symbols per span before it is closed early (192 MB of symbols)
     bool ok_ = false, stop_ = false, scan_done_ = false, finished_ = false;
     bool chain_closed_ = false;
     std::atomic<bool> speculate_{true};

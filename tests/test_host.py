@@ -507,6 +507,16 @@ def test_parallel_single_stream_inflate_equals_sequential_decode(tmp_path):
             if name == "fastq" and vn in ("l1", "l6", "l9", "huff", "sync", "full"):
                 # text in dynamic blocks: the search lines the spans up (a flush's empty stored block is decoded through)
                 assert r["spans"] > 20 and r["repairs"] <= r["spans"] // 10, (vn, r)
+    # memory bound: a span that expands beyond the soft cap is closed at a block boundary and the spans behind it
+    # are decoded from there in turn, the last one as often as it takes (TGSF_PINFLATE_SOFT_CAP is a test knob)
+    os.environ["TGSF_PINFLATE_SOFT_CAP"] = "50000"
+    try:
+        for name in ("runs", "fastq", "mixed"):
+            r = run(comp(datasets[name], 6), (name, "soft cap"))
+            assert r["size"] == len(datasets[name])
+            assert name == "runs" or r["repairs"] > 0  # ("runs" is a single block: nothing to close early)
+    finally:
+        del os.environ["TGSF_PINFLATE_SOFT_CAP"]
     z = bytearray(comp(fq[:3_000_000], 6))
     for pos in (50, 1000, len(z) // 2, len(z) - 200, len(z) - 9, len(z) - 5):  # the last two: CRC-32, ISIZE
         zz = bytearray(z)
