@@ -11,8 +11,8 @@
 // batches dealt round-robin over the GPUs) -> tgsf_collect -> records in input order (= -t 1).
 //
 // Downsampling (-g/-d/-r/-R, -F) follows DownSampleTask's selection (T.cpp:2297-2344) over the
-// filtered records.  Not in this host (SURVEY.md §8(f) "next"): BAM/SAM input (needs htslib) and
-// the HTML report; BAM is rejected with a clear message, never silently skipped.
+// filtered records.  BAM/SAM input is parsed by the ingest pipeline itself (src/pipeline.hpp; BGZF blocks decoded
+// in parallel), without htslib.
 #include <zlib.h>
 
 #include <algorithm>
@@ -235,14 +235,27 @@ string rev_comp(const string &s) { // rev_comp_seq, T.cpp:860-867
 class FastxReader {
 public:
     explicit FastxReader(const string &path) : isFastq_(file_type(path) == 1) {
+        if (file_type(path) == 2) { // BAM / SAM: the ingest parser's record reader (src/pipeline.hpp)
+            sambam_.reset(new ingest::FastParser(path, true, true));
+            if (!sambam_->ok()) sambam_.reset();
+            return;
+        }
         f_ = gzopen(path.c_str(), "rb"); // transparent for plain files, multi-member aware
         if (f_) gzbuffer(f_, 1 << 20);
         buf_.resize(1 << 20);
     }
     ~FastxReader() { if (f_) gzclose(f_); }
-    bool ok() const { return f_ != nullptr; }
+    bool ok() const { return f_ != nullptr || sambam_ != nullptr; }
     // false at end of input or on a malformed record (the reference stops there too)
     bool read(string &name, string &seq, string &qual) {
+        if (sambam_) {
+            ingest::FastParser::Rec r;
+            if (!sambam_->next(r)) return false;
+            name.assign(r.name, r.name_len);
+            seq.assign(r.seq, r.seq_len);
+            qual.assign(r.qual, r.qual_len);
+            return true;
+        }
         if (!f_) return false;
         if (isFastq_) {
             string strand;
@@ -295,6 +308,7 @@ private:
         }
     }
     gzFile f_ = nullptr;
+    std::unique_ptr<ingest::FastParser> sambam_;
     bool isFastq_;
     std::vector<char> buf_;
     size_t pos_ = 0, len_ = 0;
@@ -475,9 +489,9 @@ int main(int argc, char **argv) {
         else cerr << "Error: Please check your output file name: " << P.OutFile << endl;
         return 1;
     }
-    if (P.Infq == 2) { cerr << "Error: BAM/SAM input needs htslib, which this GPU host is not linked against." << endl; return 1; }
     if (P.Infq == 0 && P.Outfq == 1) { cerr << "Error: Fasta format input file can't output fastq format file" << endl; return 1; }
-    const bool has_qual = P.Infq == 1;
+    const bool has_qual = P.Infq == 1 || P.Infq == 2; // BAM/SAM records carry qualities (read_bam, T.cpp:1872-1916)
+    const bool sambam = P.Infq == 2;
 
     // ---- pre-pass: read_fastx (T.cpp:949-982) + Get_qType (T.cpp:1042-1077) -----------------------
     int checkLen = std::max(std::max(P.EndLen, P.BCLen), 100);
@@ -510,14 +524,14 @@ int main(int argc, char **argv) {
         auto warm_up = [&]() { Timer tw; void *warm = nullptr; if (tgsf_host_alloc(&warm, 1 << 20) == TGSF_OK) tgsf_host_free(warm); tlog("  CUDA context warm-up", tw.lap()); };
         if (init_first) warm_up();
         start_readers = [&]() -> bool {
-            if (!ingest::ParallelReader::is_gzip(P.InFile) && !getenv("TGSF_SERIAL_READER")) {
+            if (!sambam && !ingest::ParallelReader::is_gzip(P.InFile) && !getenv("TGSF_SERIAL_READER")) {
                 const int hw = (int)std::thread::hardware_concurrency();
                 const int nthr = getenv("TGSF_PARSE_THREADS") ? atoi(getenv("TGSF_PARSE_THREADS")) : std::max(1, std::min(8, hw - 2));
                 preader.reset(new ingest::ParallelReader(P.InFile, has_qual, 2 * batch_bases, nthr, &batch_pool));
                 return preader->ok();
             }
             reader_stop.store(false);
-            reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool, &reader_stop);
+            reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool, &reader_stop, sambam);
             return true;
         };
         if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
@@ -1324,7 +1338,7 @@ int main(int argc, char **argv) {
         tgsf_ctx *qctx = nullptr;
         if (tgsf_create(0, &qp, &qctx) != TGSF_OK) die_tgsf("tgsf_create (downsample QC)");
         Batch qb;
-        const bool dqual = file_type(downInput) == 1;
+        const bool dqual = file_type(downInput) == 1 || file_type(downInput) == 2;
         auto flush = [&]() {
             if (!qb.n()) return;
             if (!qb.pack()) die_tgsf("tgsf_pack_bases");

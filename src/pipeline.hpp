@@ -67,7 +67,7 @@ private:
 
 class FastParser {
 public:
-    FastParser(const std::string &path, bool fastq) : fastq_(fastq) {
+    FastParser(const std::string &path, bool fastq, bool sambam = false) : fastq_(fastq), sambam_(sambam) {
         // plain files are read with read(2) straight into the parse buffer; gzip goes through zlib
         FILE *probe = fopen(path.c_str(), "rb");
         unsigned char magic[2] = {0, 0};
@@ -130,6 +130,7 @@ public:
 
     // Views stay valid until the next call.  false: end of input (or a malformed record).
     bool next(Rec &r) {
+        if (sambam_) return next_sambam(r);
         while (true) {
             size_t p = pos_, lp[4] = {0, 0, 0, 0}, ln[4] = {0, 0, 0, 0};
             int rc = line_at(p, lp[0], ln[0]);
@@ -182,6 +183,109 @@ public:
     }
 
 private:
+    // ---- BAM / SAM input (read_bam, T.cpp:1872-1916: every record whatever its flags, name = QNAME, bases through
+    // the reference's 16-entry table {=,M,R,S,V,W,Y,H,K,D,B -> NUL; A C G T N}, quality byte + 33).  The
+    // reference reads these through htslib, which is not linked here: BAM is BGZF (decoded by the readers
+    // above, in parallel) around the little-endian records of the SAM specification section 4.2; the container is
+    // recognised from the decoded bytes ("BAM\1", else SAM text), as hts_open does.
+    bool ensure(size_t n) { // at least n unread bytes in the buffer
+        while (len_ - pos_ < n) {
+            if (eof_) return false;
+            refill();
+        }
+        return true;
+    }
+    uint32_t rd32(size_t at) const { uint32_t v; memcpy(&v, buf_.data() + at, 4); return v; }
+    bool next_sambam(Rec &r) {
+        static const char kBase[16] = {0, 'A', 'C', 0, 'G', 0, 0, 0, 'T', 0, 0, 0, 0, 0, 0, 'N'}; // T.cpp:31
+        if (sb_state_ == 0) {
+            if (!ensure(4)) return false;
+            if (memcmp(buf_.data() + pos_, "BAM\1", 4) == 0) {
+                if (!ensure(8)) return false;
+                const size_t l_text = rd32(pos_ + 4);
+                if (!ensure(12 + l_text)) return false;
+                const uint32_t n_ref = rd32(pos_ + 8 + l_text);
+                pos_ += 12 + l_text;
+                for (uint32_t i = 0; i < n_ref; ++i) {
+                    if (!ensure(4)) return false;
+                    const size_t l_name = rd32(pos_);
+                    if (!ensure(8 + l_name)) return false;
+                    pos_ += 8 + l_name;
+                }
+                sb_state_ = 1;
+            } else {
+                sb_state_ = 2;
+                for (int c = 0; c < 256; ++c) sam_code_[c] = 15; // seq_nt16_table: unknown characters read as N
+                const char *codes = "=ACMGRSVTWYHKDBN";
+                for (int i = 0; i < 16; ++i) {
+                    sam_code_[(unsigned char)codes[i]] = (uint8_t)i;
+                    sam_code_[(unsigned char)tolower(codes[i])] = (uint8_t)i;
+                }
+            }
+        }
+        if (sb_state_ == 1) { // BAM record: block_size, 32 fixed bytes, name, cigar, 4-bit bases, qualities, tags
+            if (!ensure(4)) return false;
+            const size_t bs = rd32(pos_);
+            if (bs < 32 || !ensure(4 + bs)) return false; // corrupt or truncated: sam_read1 < 0 ends the reference's loop too
+            const uint8_t *p = (const uint8_t *)buf_.data() + pos_ + 4;
+            const size_t l_name = p[8], n_cigar = (size_t)p[12] | ((size_t)p[13] << 8), l_seq = rd32(pos_ + 4 + 16);
+            const size_t off = 32 + l_name + 4 * n_cigar;
+            if ((l_seq >> 31) || off + (l_seq + 1) / 2 + l_seq > bs) return false;
+            r.name = (const char *)p + 32;
+            r.name_len = strnlen(r.name, l_name);
+            sb_seq_.resize(l_seq);
+            sb_qual_.resize(l_seq);
+            const uint8_t *sq = p + off, *ql = sq + (l_seq + 1) / 2;
+            for (size_t i = 0; i + 1 < l_seq; i += 2) {
+                sb_seq_[i] = kBase[sq[i >> 1] >> 4];
+                sb_seq_[i + 1] = kBase[sq[i >> 1] & 15];
+            }
+            if (l_seq & 1) sb_seq_[l_seq - 1] = kBase[sq[l_seq >> 1] >> 4];
+            for (size_t i = 0; i < l_seq; ++i) sb_qual_[i] = (char)(ql[i] + 33);
+            pos_ += 4 + bs;
+        } else { // SAM line: QNAME FLAG RNAME POS MAPQ CIGAR RNEXT PNEXT TLEN SEQ QUAL [tags]
+            size_t lp = 0, ln = 0;
+            while (true) {
+                size_t p = pos_;
+                const int rc = line_at(p, lp, ln);
+                if (rc == 0) { refill(); continue; }
+                if (rc < 0) return false;
+                pos_ = p;
+                if (ln == 0 || buf_[lp] == '@') continue; // header
+                break;
+            }
+            const char *f[12];
+            size_t nf = 0;
+            const char *line = buf_.data() + lp, *lend = line + ln;
+            f[nf++] = line;
+            for (const char *c = line; c < lend && nf < 12; ++c)
+                if (*c == '\t') f[nf++] = c + 1;
+            if (nf < 11) return false; // sam_parse1 fails: the reference stops reading here
+            const char *qend = nf > 11 ? f[11] - 1 : lend;
+            r.name = f[0];
+            r.name_len = (size_t)(f[1] - 1 - f[0]);
+            const char *sq = f[9];
+            size_t l_seq = (size_t)(f[10] - 1 - f[9]);
+            const char *ql = f[10];
+            const size_t l_qual = (size_t)(qend - ql);
+            if (l_seq == 1 && sq[0] == '*') l_seq = 0;
+            const bool no_qual = l_qual == 1 && ql[0] == '*';
+            if (!no_qual && l_qual != l_seq) return false; // "SEQ and QUAL are of different length"
+            sb_seq_.resize(l_seq);
+            sb_qual_.resize(l_seq);
+            for (size_t i = 0; i < l_seq; ++i) sb_seq_[i] = kBase[sam_code_[(unsigned char)sq[i]]];
+            for (size_t i = 0; i < l_seq; ++i) sb_qual_[i] = no_qual ? (char)(0xFF + 33) : ql[i]; // (q - 33) + 33
+        }
+        r.seq = sb_seq_.data();
+        r.seq_len = sb_seq_.size();
+        r.qual = sb_qual_.data();
+        r.qual_len = sb_qual_.size();
+        return true;
+    }
+    int sb_state_ = 0; // 0: container not looked at yet, 1: BAM records, 2: SAM lines
+    std::vector<char> sb_seq_, sb_qual_;
+    uint8_t sam_code_[256];
+
     // Line starting at p: [lp, lp+n) without its terminator; advances p.  1 = line, 0 = incomplete
     // (more input needed), -1 = end of data.  At EOF an unterminated tail counts as a line.
     int line_at(size_t &p, size_t &lp, size_t &n) {
@@ -258,7 +362,7 @@ private:
     std::mutex spare_m_;
     std::vector<std::unique_ptr<std::vector<char>>> spare_;
     int fd_ = -1;
-    bool fastq_, eof_ = false;
+    bool fastq_, sambam_ = false, eof_ = false;
     std::vector<char> buf_;
     size_t pos_ = 0, len_ = 0;
 };
@@ -289,8 +393,9 @@ private:
 };
 
 inline void reader_main(const std::string &path, bool fastq, uint64_t batch_bases,
-                        Queue<std::unique_ptr<RawBatch>> *out, BatchPool *pool, const std::atomic<bool> *stop = nullptr) {
-    FastParser ps(path, fastq);
+                        Queue<std::unique_ptr<RawBatch>> *out, BatchPool *pool, const std::atomic<bool> *stop = nullptr,
+                        bool sambam = false) {
+    FastParser ps(path, fastq, sambam);
     auto fresh = [&]() {
         std::unique_ptr<RawBatch> nb = pool->get();
         nb->bases.reserve((size_t)batch_bases + (batch_bases >> 2));

@@ -1,5 +1,6 @@
 // CPU check of src/pipeline.hpp: the parallel chunk parser must deliver the same records, in the
 // same order, as the serial reader.  usage: ingest_check <file> <fastq 0|1> <chunk_bytes> <threads>
+// INGEST_ONLY=serial|parallel: run one side only (digest printed, exit 0); INGEST_SAMBAM=1: the serial side reads BAM/SAM.
 #include "../../src/pipeline.hpp"
 #include <cstdio>
 
@@ -36,7 +37,7 @@ int main(int argc, char **argv) {
     if (!only || !strcmp(only, "serial")) {
         ingest::Queue<std::unique_ptr<ingest::RawBatch>> q(4);
         ingest::BatchPool pool;
-        std::thread t([&] { ingest::reader_main(path, fastq, chunk, &q, &pool); });
+        std::thread t([&] { ingest::reader_main(path, fastq, chunk, &q, &pool, nullptr, getenv("INGEST_SAMBAM") != nullptr); });
         while (auto rb = q.pop()) { a.add(*rb); pool.put(std::move(rb)); }
         t.join();
     }

@@ -801,3 +801,24 @@ def test_host_cli_parallel_single_stream_gzip_input(monkeypatch):
     assert rc0 == 0 and rc1 == 0 and rc2 == 0, (err0, err1, err2)
     assert out1 == out0 and out2 == out0 and len(out0) > 100000
     assert _info(err1) == _info(err0) and _info(err2) == _info(err0)
+
+
+def test_host_cli_bam_and_sam_input(monkeypatch):
+    """BAM / SAM input (read_bam, T.cpp:984-1040 pre-pass sampling and 1872-1916 main pass): the CLI parses the
+    records itself (src/pipeline.hpp, BGZF blocks in parallel) and must write the records and INFO lines it writes
+    for the equivalent FASTQ; the reference CLI (htslib) on the same BAM must agree where it is available."""
+    import bam_lib
+    import ref_lib
+    fq = synth.make_config(2, 200, max_len=30000, with_names=False).to_fastq()
+    bam, sam = bam_lib.from_fastq(fq)
+    rc0, out0, err0 = _run_host_cli(["-x", "ont"], fq)
+    rc1, out1, err1 = _run_host_cli(["-x", "ont"], bam, in_name="in.bam")
+    rc2, out2, err2 = _run_host_cli(["-x", "ont"], sam, in_name="in.sam")
+    monkeypatch.setenv("TGSF_BATCH_MB", "1")
+    rc3, out3, err3 = _run_host_cli(["-x", "ont"], bam, in_name="in.bam")
+    assert rc0 == 0 and rc1 == 0 and rc2 == 0 and rc3 == 0, (err0, err1, err2, err3)
+    assert len(out0) > 100000 and out1 == out0 and out2 == out0 and out3 == out0
+    assert _info(err1) == _info(err0) and _info(err2) == _info(err0) and _info(err3) == _info(err0)
+    if ref_lib.available():
+        r_rc, r_out, r_err, _ = ref_lib.run_cli(["-x", "ont", "-t", "1"], bam, in_name="in.bam")
+        assert r_rc == 0 and r_out == out1 and _info(r_err) == _info(err1)

@@ -529,6 +529,74 @@ def test_parallel_single_stream_inflate_equals_sequential_decode(tmp_path):
     run(bytes(z), "default and oversized span", threads=("4",), span="16777216")
 
 
+def test_bam_and_sam_ingest_equals_fastq(tmp_path):
+    """BAM / SAM input (read_bam, T.cpp:1872-1916) is parsed by src/pipeline.hpp without htslib: the records must
+    equal those of the equivalent FASTQ — every record whatever its flags, bases through the reference's nibble
+    table (lower case folded, ambiguity codes and '=' -> NUL, unknown -> N), quality + 33 (absent: 0xFF + 33 = ' '),
+    zero-length records kept.  Where the compiled reference is available its htslib must accept the test files:
+    the reference CLI gives the same records and INFO lines for the BAM, the SAM and the FASTQ."""
+    import subprocess
+    import bam_lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "ingest_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(3)
+
+    def digest(path, sambam, threads="4", chunk="3000000"):
+        env = dict(os.environ, INGEST_ONLY="serial", INGEST_HASH="1", TGSF_INFLATE_THREADS=threads)
+        if sambam:
+            env["INGEST_SAMBAM"] = "1"
+        r = subprocess.run([exe, path, "1", chunk, "1"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.split()[:3]
+
+    def write(name, blob):
+        path = str(tmp_path / name)
+        with open(path, "wb") as f:
+            f.write(blob)
+        return path
+
+    recs, sam, fq = [], [b"@HD\tVN:1.6\n", b"@PG\tID:x\n"], []
+    for i in range(1200):
+        ln = int(rng.integers(1, 4)) if i % 300 == 7 else int(rng.integers(50, 30000))
+        seq = "".join(rng.choice(list("ACGT"), ln))
+        if i % 10 == 0 and ln > 20:
+            s = list(seq)
+            for p in rng.integers(0, ln, 5):
+                s[int(p)] = "NacgtnRY=xM"[int(rng.integers(0, 11))]
+            seq = "".join(s)
+        qual = None if i % 400 == 3 else rng.integers(0, 60, ln).astype(np.uint8)
+        name = "m64011_%d/ccs" % i
+        recs.append(bam_lib.bam_record(name, seq, qual, flag=(4, 0, 16, 256, 2048)[i % 5], tags=b"RGZgrp\0" if i % 3 else b""))
+        sam.append(bam_lib.sam_line(name, seq, qual, tags="RG:Z:grp" if i % 3 else ""))
+        q33 = b" " * ln if qual is None else bytes(qual + 33)
+        fq.append(b"@" + name.encode() + b"\n" + bam_lib.through_reference_table(seq) + b"\n+\n" + q33 + b"\n")
+    bam = write("x.bam", bam_lib.bam_file(recs, refs=(("chr1", 1000), ("chrUn_with_a_long_name", 5))))
+    want = digest(write("x.fq", b"".join(fq)), False)
+    assert want[0] == "1200"
+    assert digest(bam, True) == want and digest(bam, True, threads="1") == want and digest(bam, True, chunk="20000") == want
+    assert digest(write("x.sam", b"".join(sam)), True) == want
+    # zero-length records (SEQ '*') stay in the stream; a truncated BAM ends the input at the last whole record
+    recs0 = [bam_lib.bam_record("a", "ACGT", [1, 2, 3, 4]), bam_lib.bam_record("empty", "", []), bam_lib.bam_record("b", "GG", None)]
+    sam0 = bam_lib.sam_line("a", "ACGT", [1, 2, 3, 4]) + bam_lib.sam_line("empty", "", None) + bam_lib.sam_line("b", "GG", None)
+    d0 = digest(write("z.bam", bam_lib.bam_file(recs0)), True)
+    assert d0[:2] == ["3", "6"] and digest(write("z.sam", sam0), True) == d0
+    import zlib
+    raw = b"BAM\1" + (0).to_bytes(4, "little") * 2 + b"".join(recs0)
+    assert digest(write("t.bam", bam_lib.bgzf(raw[:-3])), True)[:2] == ["2", "4"]
+    assert digest(write("e.bam", bam_lib.bam_file([])), True)[:2] == ["0", "0"]
+    import ref_lib
+    if ref_lib.available():
+        clean = synth.make_config(2, 60, max_len=20000, with_names=False).to_fastq()
+        b2, s2 = bam_lib.from_fastq(clean)
+        outs = [ref_lib.run_cli(["-x", "ont", "-t", "1"], blob, in_name=nm) for nm, blob in (("in.fq", clean), ("in.bam", b2), ("in.sam", s2))]
+        info = [[l for l in o[2].splitlines() if l.startswith("INFO") and "written to" not in l] for o in outs]
+        assert outs[0][0] == 0 and len(outs[0][1]) > 10000
+        assert outs[1][1] == outs[0][1] and outs[2][1] == outs[0][1] and info[1] == info[0] and info[2] == info[0]
+        assert digest(write("c.bam", b2), True) == digest(write("c.fq", clean), False) == digest(write("c.sam", s2), True)
+
+
 def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
     """tgsfilter_b200/csrc/gzenc_core.h (code lengths, canonical codes, dynamic block header — the serial half
     of the GPU deflate encoder) built for the host: members assembled from it must inflate with zlib to the
