@@ -236,10 +236,17 @@ private:
             sb_seq_.resize(l_seq);
             sb_qual_.resize(l_seq);
             const uint8_t *sq = p + off, *ql = sq + (l_seq + 1) / 2;
-            for (size_t i = 0; i + 1 < l_seq; i += 2) {
-                sb_seq_[i] = kBase[sq[i >> 1] >> 4];
-                sb_seq_[i + 1] = kBase[sq[i >> 1] & 15];
-            }
+            static const struct Pairs { // packed byte -> its two bases
+                uint16_t v[256];
+                Pairs() {
+                    for (int b = 0; b < 256; ++b) {
+                        const char two[2] = {kBase[b >> 4], kBase[b & 15]};
+                        memcpy(&v[b], two, 2);
+                    }
+                }
+            } pairs;
+            char *dst = sb_seq_.data();
+            for (size_t i = 0; i < l_seq / 2; ++i) memcpy(dst + 2 * i, &pairs.v[sq[i]], 2);
             if (l_seq & 1) sb_seq_[l_seq - 1] = kBase[sq[l_seq >> 1] >> 4];
             for (size_t i = 0; i < l_seq; ++i) sb_qual_[i] = (char)(ql[i] + 33);
             pos_ += 4 + bs;
