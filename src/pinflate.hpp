@@ -14,7 +14,9 @@
 //      where span i-1 ended (span 0 starts at the member's first block), so an accepted chain IS the
 //      sequential decode — speculation only ever decides how fast the answer comes.  A span that does not
 //      line up (block search fooled, stored/fixed block at the boundary, non-text data) is decoded again
-//      from the known boundary.  With the previous span's last 32 KB resolved, the placeholders are
+//      from the known boundary — as plain bytes, since its window is known by then (so are span 0 and, once
+//      the search has failed twice or four spans in a row had to be redone, every span: the speed of the
+//      sequential decoder is the floor).  With the previous span's last 32 KB resolved, the placeholders are
 //      replaced through a 33 K-entry lookup table and the span's CRC-32 is taken, both on the workers;
 //      the consumer combines the CRCs (crc32_combine) and checks the member trailer.
 // A large member behind this one (`cat a.fq.gz b.fq.gz`) gets a reader of its own; small remainders and
@@ -139,10 +141,11 @@ public:
     BitIn b;
 
     // First bit position in [from, to) that starts a plausible non-final dynamic block; (uint64_t)-1 if none.
-    uint64_t find_block(const uint8_t *base, size_t size, uint64_t from, uint64_t to) {
+    uint64_t find_block(const uint8_t *base, size_t size, uint64_t from, uint64_t to, const std::atomic<bool> *abort = nullptr) {
         const uint64_t last = size >= 16 ? 8ull * (size - 16) : 0; // the peek below reads 8 bytes
         to = std::min(to, last);
         for (uint64_t bit = from; bit < to; ++bit) {
+            if ((bit & 8191) == 0 && abort && abort->load(std::memory_order_relaxed)) break;
             uint64_t w;
             memcpy(&w, base + (bit >> 3), 8);
             w >>= bit & 7;
@@ -189,8 +192,10 @@ public:
         return nullptr;
     }
 
-    // Stored block body (cursor just behind the 3 header bits): widened into out.  Needs room for 65535 symbols.
-    const char *stored_block(uint16_t *&out) {
+    // Stored block body (cursor just behind the 3 header bits) copied (widened for 16-bit symbols) into out.
+    // Needs room for 65535 symbols.
+    template <typename T>
+    const char *stored_block(T *&out) {
         b.take(b.bc & 7);
         const uint64_t byte = b.bitpos() >> 3;
         const size_t size = (size_t)(b.end - b.base);
@@ -207,8 +212,11 @@ public:
 
     // Huffman block body.  1: end of block, 0: out reached out_lim (call again with more room), -1: error (err set).
     // out_lim must leave MARGIN symbols of room behind it; out - 32768 must be addressable.
-    int huffman_block(uint16_t *&out_ref, uint16_t *out_lim, const char *&err) {
-        uint16_t *out = out_ref;
+    // T = uint16_t: symbols, the unknown window in front of the span is placeholders (no distance check needed);
+    // T = uint8_t: bytes behind a known window, a match may not reach below `floor` (first valid byte).
+    template <typename T>
+    int huffman_block(T *&out_ref, T *out_lim, const T *floor, const char *&err) {
+        T *out = out_ref;
         uint64_t bb = b.bb;
         unsigned bc = b.bc;
         const uint8_t *in = b.in;
@@ -240,8 +248,13 @@ public:
 #define PGZ_EMIT()                                                                                          \
     do {                                                                                                    \
         const uint64_t l_ = m & 0xFFFFFFu;                                                                  \
-        const uint64_t w_ = (l_ & 0xFF) | ((l_ & 0xFF00) << 8) | ((l_ & 0xFF0000) << 16);                   \
-        memcpy(out, &w_, 8);                                                                                \
+        if (sizeof(T) == 2) {                                                                               \
+            const uint64_t w_ = (l_ & 0xFF) | ((l_ & 0xFF00) << 8) | ((l_ & 0xFF0000) << 16);               \
+            memcpy(out, &w_, 8);                                                                            \
+        } else {                                                                                            \
+            const uint32_t w_ = (uint32_t)l_;                                                               \
+            memcpy(out, &w_, 4);                                                                            \
+        }                                                                                                   \
         out += (m >> 28) & 3u;                                                                              \
         const unsigned nb_ = (m >> 24) & 15u;                                                               \
         bb >>= nb_;                                                                                         \
@@ -278,7 +291,7 @@ public:
                 e = lit[e.val + (bb & ((1u << (e.op & 15)) - 1))];
             }
             bb >>= e.nbits; bc -= e.nbits;
-            if (e.op == 0) { *out++ = e.val; continue; }
+            if (e.op == 0) { *out++ = (T)e.val; continue; }
             if (e.op & 0x40) { ret = 1; break; }
             if (!(e.op & 0x10)) { err = "invalid literal/length code"; ret = -1; break; }
             unsigned len = e.val, xb = e.op & 15;
@@ -295,19 +308,24 @@ public:
             xb = d.op & 15;
             const unsigned distance = d.val + (unsigned)(bb & ((1u << xb) - 1)); // <= 32768 by the tables
             bb >>= xb; bc -= xb;
-            const uint16_t *src = out - distance;
-            uint16_t *const stop = out + len;
-            if (distance >= 8) { // 16-byte copies; may write up to 15 symbols past stop (SLACK)
+            if (sizeof(T) == 1 && distance > (size_t)(out - floor)) { err = "invalid match distance"; ret = -1; break; }
+            const T *src = out - distance;
+            T *const stop = out + len;
+            if (distance >= 16 / sizeof(T)) { // 16-byte copies; may write up to 16 bytes past stop (SLACK)
                 memcpy(out, src, 16);
-                memcpy(out + 8, src + 8, 16);
-                if (len > 16) {
-                    out += 16;
-                    src += 16;
-                    do { memcpy(out, src, 16); out += 8; src += 8; } while (out < stop);
+                memcpy(out + 16 / sizeof(T), src + 16 / sizeof(T), 16);
+                if (len > 32 / sizeof(T)) {
+                    out += 32 / sizeof(T);
+                    src += 32 / sizeof(T);
+                    do { memcpy(out, src, 16); out += 16 / sizeof(T); src += 16 / sizeof(T); } while (out < stop);
                 }
-            } else if (distance == 1) { // a run: 8 symbols per step, up to 7 past stop
-                const uint64_t v4 = (uint64_t)*src * 0x0001000100010001ull;
-                do { memcpy(out, &v4, 8); memcpy(out + 4, &v4, 8); out += 8; } while (out < stop);
+            } else if (distance == 1) { // a run
+                if (sizeof(T) == 1) {
+                    memset(out, (int)*src, len);
+                } else {
+                    const uint64_t v4 = (uint64_t)*src * 0x0001000100010001ull;
+                    do { memcpy(out, &v4, 8); memcpy(out + 4, &v4, 8); out += 8; } while (out < stop);
+                }
             } else {
                 do { *out++ = *src++; } while (out < stop);
             }
@@ -464,7 +482,7 @@ public:
             lk.unlock();
             if (!t.discard) {
                 const size_t k = std::min(n - got, t.nout - t.pos);
-                memcpy(d + got, t.out.get() + t.pos, k);
+                memcpy(d + got, t.bytes + t.pos, k);
                 t.pos += k;
                 got += k;
                 if (t.pos < t.nout) continue;
@@ -473,6 +491,7 @@ public:
                 if (t.err) { error_ = t.err; break; }
                 if (t.final) { finish_member(t.end_bit); continue; }
             }
+            release_sym(t);
             lk.lock();
             tasks_.pop_front();
             ++front_idx_;
@@ -489,6 +508,8 @@ private:
         size_t idx = 0;
         uint64_t stop_bit = 0, start_bit = 0, end_bit = 0;
         bool known_start = false, found = false, final = false, discard = false;
+        bool direct = false; // decoded as bytes behind a known window (no placeholders)
+        const uint8_t *bytes = nullptr; // the span's output once READY
         std::atomic<bool> cancel{false};
         const char *err = nullptr;
         uint16_t *sym = nullptr; // HIST placeholders, then the decoded symbols
@@ -526,6 +547,7 @@ private:
         {
             std::lock_guard<std::mutex> lk(m_);
             stop_ = true;
+            abort_search_.store(true);
             for (auto &t : tasks_) t->cancel.store(true);
         }
         cv_.notify_all();
@@ -575,10 +597,10 @@ private:
         t.sym = nullptr;
         t.sym_cap = 0;
     }
-    void grow_sym(Task &t, size_t used) {
+    void grow_sym(Task &t, size_t used_bytes) {
         const size_t cap = t.sym_cap + t.sym_cap / 2;
         uint16_t *n = new uint16_t[cap];
-        memcpy(n, t.sym, used * sizeof(uint16_t));
+        memcpy(n, t.sym, used_bytes);
         delete[] t.sym;
         t.sym = n;
         t.sym_cap = cap;
@@ -591,8 +613,12 @@ private:
         uint64_t v = f.load();
         if (v == UNKNOWN && f.compare_exchange_strong(v, SEARCHING)) {
             const uint64_t from = 8ull * (data0_ + idx * span_);
-            v = D.find_block(base_, size_, from, from + 8ull * 4 * span_);
-            if (v == (uint64_t)-1) v = NOT_FOUND;
+            // a span without a block start in it (blocks of several MB, one-block streams) is left to the chain
+            v = D.find_block(base_, size_, from, from + 8ull * span_, &abort_search_);
+            if (v == (uint64_t)-1) {
+                v = NOT_FOUND;
+                if (++not_found_ >= 2) { speculate_.store(false); abort_search_.store(true); } // searching does not pay here
+            }
             f.store(v);
             return v;
         }
@@ -615,8 +641,29 @@ private:
         }
         const auto c1 = std::chrono::steady_clock::now();
         if (!t.sym) acquire_sym(t, HIST + 5 * span_ + MARGIN);
-        for (size_t j = 0; j < HIST; ++j) t.sym[j] = (uint16_t)(256 + j);
-        uint16_t *out = t.sym + HIST;
+        if (t.direct) decode_blocks<uint8_t>(t, D);
+        else decode_blocks<uint16_t>(t, D);
+        phase_ns_[1] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - c1).count();
+    }
+
+    // T = uint16_t: the window in front of the span is unknown (placeholders); T = uint8_t ("direct"): the chain
+    // has already reached this span's start (span 0, a span decoded again, sequential mode), so its window is known
+    // and the bytes are final as they are written — the speed of the sequential decoder.
+    template <typename T>
+    void decode_blocks(Task &t, pinf::SymDecoder &D) {
+        using namespace pinf;
+        T *buf = (T *)t.sym;
+        size_t cap = t.sym_cap * sizeof(uint16_t) / sizeof(T);
+        if (sizeof(T) == 2) for (size_t j = 0; j < HIST; ++j) buf[j] = (T)(256 + j);
+        else memcpy(buf, t.win.data(), HIST);
+        T *out = buf + HIST;
+        auto grow = [&]() {
+            const size_t used = (size_t)(out - buf);
+            grow_sym(t, used * sizeof(T));
+            buf = (T *)t.sym;
+            cap = t.sym_cap * sizeof(uint16_t) / sizeof(T);
+            out = buf + used;
+        };
         D.b.seek(base_, size_, t.start_bit);
         bool final = false;
         while (!final) {
@@ -631,28 +678,22 @@ private:
             }
             // Memory bound for streams that expand enormously (a span of 2 MB can hold GBs of runs): close the
             // span at this boundary; the spans behind it no longer line up and are decoded from here in turn.
-            if ((size_t)(out - t.sym) - HIST >= soft_cap_) break;
+            if ((size_t)(out - buf) - HIST >= soft_cap_) break;
             if (t.cancel.load(std::memory_order_relaxed)) return;
             unsigned type;
             if ((t.err = D.block_header(final, type))) break;
             if (type == 0) {
-                const size_t used = (size_t)(out - t.sym);
-                if (used + 65536 + MARGIN > t.sym_cap) { grow_sym(t, used); out = t.sym + used; }
+                if ((size_t)(out - buf) + 65536 + MARGIN > cap) grow();
                 if ((t.err = D.stored_block(out))) break;
                 continue;
             }
             int r;
-            while ((r = D.huffman_block(out, t.sym + t.sym_cap - MARGIN, t.err)) == 0) {
-                const size_t used = (size_t)(out - t.sym);
-                grow_sym(t, used);
-                out = t.sym + used;
-            }
+            while ((r = D.huffman_block<T>(out, buf + cap - MARGIN, buf + HIST - t.win_valid, t.err)) == 0) grow();
             if (r < 0) break;
         }
         t.final = final && !t.err;
         t.end_bit = D.b.bitpos();
-        t.nsym = (size_t)(out - t.sym) - HIST;
-        phase_ns_[1] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - c1).count();
+        t.nsym = (size_t)(out - buf) - HIST;
     }
 
     // ---- chain validation (m_ held): accept spans in order, hand the window on ----
@@ -672,9 +713,12 @@ private:
             if (!lined_up) { // decode again from the boundary the chain has proven
                 t.known_start = true;
                 t.start_bit = chain_end_bit_;
+                t.direct = true; // the window is known now
+                t.win = chain_window_;
+                t.win_valid = chain_valid_;
                 t.state = QUEUED;
                 ++repairs_;
-                if (++consecutive_repairs_ >= 4) speculate_.store(false); // the search does not work on this data
+                if (++consecutive_repairs_ >= 4) { speculate_.store(false); abort_search_.store(true); } // the search does not work on this data
                 return;
             }
             if (t.idx > 0 && !t.known_start) consecutive_repairs_ = 0;
@@ -683,10 +727,14 @@ private:
             // the window behind this span: last HIST bytes of (window | resolved symbols)
             if (t.nsym) {
                 std::vector<uint8_t> w(HIST);
-                const uint16_t *s = t.sym + HIST + t.nsym - HIST; // symbol that lands at w[0] (may lie in the prefix)
-                for (size_t j = 0; j < HIST; ++j) {
-                    const uint16_t v = s[j];
-                    w[j] = v < 256 ? (uint8_t)v : chain_window_[v - 256];
+                if (t.direct) {
+                    memcpy(w.data(), (const uint8_t *)t.sym + t.nsym, HIST); // last HIST bytes of (window | output)
+                } else {
+                    const uint16_t *s = t.sym + t.nsym; // the symbol that lands at w[0] (may lie in the placeholder prefix)
+                    for (size_t j = 0; j < HIST; ++j) {
+                        const uint16_t v = s[j];
+                        w[j] = v < 256 ? (uint8_t)v : chain_window_[v - 256];
+                    }
                 }
                 chain_window_.swap(w);
                 chain_valid_ = std::min<size_t>(HIST, chain_valid_ + t.nsym);
@@ -699,6 +747,7 @@ private:
             if (t.final || t.err) {
                 chain_closed_ = true;
                 scan_done_ = true;
+                abort_search_.store(true);
                 for (auto &o : tasks_)
                     if (o->idx > t.idx) o->cancel.store(true);
             }
@@ -711,6 +760,13 @@ private:
     void resolve_span(Task &t) {
         using namespace pinf;
         const auto c0 = std::chrono::steady_clock::now();
+        if (t.direct) { // bytes are final: only the CRC is left; the buffer is released when the consumer is done
+            t.bytes = (const uint8_t *)t.sym + HIST;
+            t.nout = t.nsym;
+            t.crc = crc_of(t.bytes, t.nout);
+            phase_ns_[2] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - c0).count();
+            return;
+        }
         t.out.reset(new uint8_t[t.nsym + 1]);
         const uint16_t *s = t.sym + HIST;
         uint8_t *o = t.out.get();
@@ -738,17 +794,21 @@ private:
         }
         for (; j < n; ++j) o[j] = L[s[j]];
         t.nout = n;
-        size_t done = 0;
-        uint32_t c = 0;
-        while (done < n) { // crc32 takes a 32-bit length
-            const size_t k = std::min<size_t>(n - done, 1u << 30);
-            c = (uint32_t)crc32(c, o + done, (uInt)k);
-            done += k;
-        }
-        t.crc = c;
+        t.bytes = o;
+        t.crc = crc_of(o, n);
         release_sym(t);
         std::vector<uint8_t>().swap(t.win);
         phase_ns_[2] += (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - c0).count();
+    }
+
+    static uint32_t crc_of(const uint8_t *p, size_t n) { // crc32 takes a 32-bit length
+        uint32_t c = 0;
+        for (size_t done = 0; done < n;) {
+            const size_t k = std::min<size_t>(n - done, 1u << 30);
+            c = (uint32_t)crc32(c, p + done, (uInt)k);
+            done += k;
+        }
+        return c;
     }
 
     Task *new_task(bool known) { // m_ held
@@ -759,6 +819,9 @@ private:
         if (t->idx == 0 || known) {
             t->known_start = true;
             t->start_bit = t->idx == 0 ? 8ull * data0_ : chain_end_bit_;
+            t->direct = true; // the chain is at this span's start: its window is known
+            t->win = chain_window_;
+            t->win_valid = chain_valid_;
         }
         if (next_idx_ >= nspans_) scan_done_ = true;
         t->state = DECODING;
@@ -808,7 +871,8 @@ private:
     size_t soft_cap_ = 96u << 20; // symbols per span before it is closed early (192 MB of symbols)
     bool ok_ = false, stop_ = false, scan_done_ = false, finished_ = false;
     bool chain_closed_ = false;
-    std::atomic<bool> speculate_{true};
+    std::atomic<bool> speculate_{true}, abort_search_{false};
+    std::atomic<unsigned> not_found_{0};
     std::unique_ptr<std::atomic<uint64_t>[]> found_;
     const char *error_ = nullptr;
     size_t next_idx_ = 0, front_idx_ = 0, chain_next_ = 0, repairs_ = 0, consecutive_repairs_ = 0;
