@@ -200,6 +200,10 @@ private:
         static const char kBase[16] = {0, 'A', 'C', 0, 'G', 0, 0, 0, 'T', 0, 0, 0, 0, 0, 0, 'N'}; // T.cpp:31
         if (sb_state_ == 0) {
             if (!ensure(4)) return false;
+            if (memcmp(buf_.data() + pos_, "CRAM", 4) == 0) {
+                std::cerr << "Error: CRAM input is not supported (convert with `samtools fastq` or to BAM)" << std::endl;
+                return false;
+            }
             if (memcmp(buf_.data() + pos_, "BAM\1", 4) == 0) {
                 if (!ensure(8)) return false;
                 const size_t l_text = rd32(pos_ + 4);
@@ -226,7 +230,8 @@ private:
         if (sb_state_ == 1) { // BAM record: block_size, 32 fixed bytes, name, cigar, 4-bit bases, qualities, tags
             if (!ensure(4)) return false;
             const size_t bs = rd32(pos_);
-            if (bs < 32 || !ensure(4 + bs)) return false; // corrupt or truncated: sam_read1 < 0 ends the reference's loop too
+            // corrupt or truncated: sam_read1 < 0 ends the reference's loop too (a record of 512 MB is not a read)
+            if (bs < 32 || bs > (512u << 20) || !ensure(4 + bs)) return false;
             const uint8_t *p = (const uint8_t *)buf_.data() + pos_ + 4;
             const size_t l_name = p[8], n_cigar = (size_t)p[12] | ((size_t)p[13] << 8), l_seq = rd32(pos_ + 4 + 16);
             const size_t off = 32 + l_name + 4 * n_cigar;
