@@ -128,6 +128,22 @@ public:
 
     struct Rec { const char *name, *seq, *qual; size_t name_len, seq_len, qual_len; };
 
+    // Decoded bytes of the input, whatever the container; <= 0 at the end (decoder errors are reported on stderr).
+    long read_source(char *dst, size_t want) {
+        const long got = ss_ ? (long)ss_->read(dst, want)
+                       : mm_ ? (long)mm_->read(dst, want)
+                       : bgzf_ ? (long)bgzf_->read(dst, want)
+                       : gz_ ? (long)read_inflated(dst, want)
+                       : f_ ? (long)gzread(f_, dst, (unsigned)want)
+                            : (long)read(fd_, dst, want);
+        if (ss_ && got == 0 && ss_->failed()) std::cerr << "Error: " << ss_->error() << " (gzip input)" << std::endl;
+        if (mm_ && got == 0 && mm_->failed()) std::cerr << "Error: " << mm_->error() << " (gzip input)" << std::endl;
+        if (bgzf_ && got == 0 && bgzf_->failed()) std::cerr << "Error: " << bgzf_->error() << " (BGZF input)" << std::endl;
+        if (gz_ && got == 0 && gz_->failed()) std::cerr << "Error: " << gz_->error() << " (gzip input)" << std::endl;
+        return got;
+    }
+    bool parallel_decoder() const { return ss_ != nullptr || mm_ != nullptr || bgzf_ != nullptr; }
+
     // Views stay valid until the next call.  false: end of input (or a malformed record).
     bool next(Rec &r) {
         if (sambam_) return next_sambam(r);
@@ -325,16 +341,7 @@ private:
         if (len_ == buf_.size()) buf_.resize(buf_.size() * 2); // one record larger than the buffer
         while (len_ < buf_.size()) {
             const size_t want = std::min<size_t>(buf_.size() - len_, 1u << 30);
-            const long got = ss_ ? (long)ss_->read(buf_.data() + len_, want)
-                           : mm_ ? (long)mm_->read(buf_.data() + len_, want)
-                           : bgzf_ ? (long)bgzf_->read(buf_.data() + len_, want)
-                           : gz_ ? (long)read_inflated(buf_.data() + len_, want)
-                           : f_ ? (long)gzread(f_, buf_.data() + len_, (unsigned)want)
-                                : (long)read(fd_, buf_.data() + len_, want);
-            if (ss_ && got == 0 && ss_->failed()) std::cerr << "Error: " << ss_->error() << " (gzip input)" << std::endl;
-            if (mm_ && got == 0 && mm_->failed()) std::cerr << "Error: " << mm_->error() << " (gzip input)" << std::endl;
-            if (bgzf_ && got == 0 && bgzf_->failed()) std::cerr << "Error: " << bgzf_->error() << " (BGZF input)" << std::endl;
-            if (gz_ && got == 0 && gz_->failed()) std::cerr << "Error: " << gz_->error() << " (gzip input)" << std::endl;
+            const long got = read_source(buf_.data() + len_, want);
             if (got <= 0) { eof_ = true; break; }
             len_ += (size_t)got;
             if (len_ >= buf_.size() / 2) break;
@@ -404,10 +411,20 @@ private:
     std::vector<std::unique_ptr<RawBatch>> free_;
 };
 
+class FastParser;
+inline void stream_reader_main(FastParser &src, bool fastq, uint64_t batch_bases, Queue<std::unique_ptr<RawBatch>> *out,
+                               BatchPool *pool, const std::atomic<bool> *stop, int threads);
+
 inline void reader_main(const std::string &path, bool fastq, uint64_t batch_bases,
                         Queue<std::unique_ptr<RawBatch>> *out, BatchPool *pool, const std::atomic<bool> *stop = nullptr,
                         bool sambam = false) {
     FastParser ps(path, fastq, sambam);
+    // opt-in (TGSF_STREAM_PARSE_THREADS=n): compressed FASTQ/FASTA decoded by a parallel reader is also parsed in parallel
+    if (const char *e = getenv("TGSF_STREAM_PARSE_THREADS"))
+        if (atoi(e) > 0 && !sambam && ps.ok() && ps.parallel_decoder()) {
+            stream_reader_main(ps, fastq, batch_bases, out, pool, stop, atoi(e));
+            return;
+        }
     auto fresh = [&]() {
         std::unique_ptr<RawBatch> nb = pool->get();
         nb->bases.reserve((size_t)batch_bases + (batch_bases >> 2));
@@ -528,7 +545,10 @@ private:
         return true;
     }
     // parse [s, e) (record aligned); false on a malformed record (same messages as the serial parser)
-    bool parse_range(const char *s, const char *e, RawBatch &b) const {
+    bool parse_range(const char *s, const char *e, RawBatch &b) const { return parse_range(fastq_, s, e, b); }
+public:
+    // parse [s, e) (record aligned) into b; false on a malformed record (same messages as the serial parser)
+    static bool parse_range(const bool fastq_, const char *s, const char *e, RawBatch &b) {
         const char *p = s;
         const char hdr = fastq_ ? '@' : '>';
         while (p < e) {
@@ -558,6 +578,7 @@ private:
         }
         return true;
     }
+private:
     void work() {
         while (true) {
             size_t ci;
@@ -596,5 +617,125 @@ private:
     std::mutex m_;
     std::condition_variable cv_;
 };
+
+// ---------------------------------------------------------------------------------------------
+// Parallel parsing of a decoded stream (gzip / BGZF input): behind the parallel decoders one parser thread is
+// the next limit (~1.6 GB/s of FASTQ on the bench host).  The reader thread copies the decoded bytes into
+// chunks, cuts each chunk at its last verified record start (a header line whose second-next line starts
+// with '+'; FASTA: a '>' line) and carries the tail over; worker threads parse the chunks with the plain-file
+// chunk parser; batches leave in stream order.  Same contract as reader_main (nullptr ends the stream; the
+// records in front of a malformed one are still delivered).
+// ---------------------------------------------------------------------------------------------
+inline size_t last_record_start(const char *b, size_t len, bool fastq) { // 0: none (or only the buffer start)
+    const char hdr = fastq ? '@' : '>';
+    size_t e = len;
+    while (true) {
+        const void *q = e ? memrchr(b, '\n', e) : nullptr; // last newline in [0, e)
+        const size_t ls = q ? (size_t)((const char *)q - b) + 1 : 0;
+        if (ls > 0 && ls < len && b[ls] == hdr) {
+            if (!fastq) return ls;
+            const char *l1 = (const char *)memchr(b + ls, '\n', len - ls);
+            const char *l2 = l1 ? (const char *)memchr(l1 + 1, '\n', len - (size_t)(l1 + 1 - b)) : nullptr;
+            if (l2 && (size_t)(l2 + 1 - b) < len && l2[1] == '+') return ls;
+        }
+        if (!q) return 0;
+        e = ls - 1;
+    }
+}
+
+inline void stream_reader_main(FastParser &src, bool fastq, uint64_t batch_bases, Queue<std::unique_ptr<RawBatch>> *out,
+                               BatchPool *pool, const std::atomic<bool> *stop, int threads) {
+    struct Job {
+        std::vector<char> buf;
+        size_t len = 0;
+        std::unique_ptr<RawBatch> batch;
+        int state = 0; // 1 parsed, 2 parsed up to a malformed record
+    };
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<Job *> todo;
+    bool quit = false;
+    std::vector<std::thread> workers;
+    for (int t = 0; t < std::max(1, threads); ++t)
+        workers.emplace_back([&] {
+            while (true) {
+                Job *j;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return quit || !todo.empty(); });
+                    if (todo.empty()) return;
+                    j = todo.front();
+                    todo.pop_front();
+                }
+                j->batch = pool->get();
+                j->batch->bases.reserve(j->len / (fastq ? 2 : 1) + 1024);
+                if (fastq) j->batch->quals.reserve(j->len / 2 + 1024);
+                const bool good = ParallelReader::parse_range(fastq, j->buf.data(), j->buf.data() + j->len, *j->batch);
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    j->state = good ? 1 : 2;
+                }
+                cv.notify_all();
+            }
+        });
+    const size_t chunk = std::max<size_t>(1u << 20, (size_t)(fastq ? 2 * batch_bases : batch_bases));
+    const size_t window = (size_t)std::max(1, threads) + 2;
+    std::deque<std::unique_ptr<Job>> inflight;
+    std::vector<std::unique_ptr<Job>> spare;
+    std::vector<char> carry;
+    bool eof = false, ended = false; // ended: malformed record or stop request — nothing more is delivered
+    auto deliver_front = [&]() {     // wait for the oldest chunk, hand its batch on
+        Job *j = inflight.front().get();
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv.wait(lk, [&] { return j->state != 0; });
+        }
+        if (!ended) {
+            if (j->batch && j->batch->n()) out->push(std::move(j->batch));
+            if (j->state == 2 || (stop && stop->load())) ended = true;
+        }
+        if (j->batch) pool->put(std::move(j->batch));
+        j->state = 0;
+        spare.push_back(std::move(inflight.front()));
+        inflight.pop_front();
+    };
+    while (!eof && !ended) {
+        std::unique_ptr<Job> j;
+        if (!spare.empty()) { j = std::move(spare.back()); spare.pop_back(); }
+        else j.reset(new Job());
+        if (j->buf.size() < chunk + carry.size()) j->buf.resize(chunk + carry.size());
+        memcpy(j->buf.data(), carry.data(), carry.size());
+        size_t len = carry.size(), cut = 0;
+        while (true) {
+            while (len < j->buf.size()) {
+                const long got = src.read_source(j->buf.data() + len, std::min<size_t>(j->buf.size() - len, 1u << 30));
+                if (got <= 0) { eof = true; break; }
+                len += (size_t)got;
+            }
+            cut = eof ? len : last_record_start(j->buf.data(), len, fastq);
+            if (eof || cut > 0) break;
+            j->buf.resize(j->buf.size() * 2); // one record longer than the chunk
+        }
+        carry.assign(j->buf.data() + cut, j->buf.data() + len);
+        j->len = cut;
+        Job *raw = j.get();
+        inflight.push_back(std::move(j));
+        {
+            std::lock_guard<std::mutex> lk(m);
+            todo.push_back(raw);
+        }
+        cv.notify_all();
+        while (!inflight.empty() && (inflight.size() > window || [&] { std::lock_guard<std::mutex> lk(m); return inflight.front()->state != 0; }()))
+            deliver_front();
+    }
+    while (!inflight.empty()) deliver_front();
+    {
+        std::lock_guard<std::mutex> lk(m);
+        quit = true;
+    }
+    cv.notify_all();
+    for (auto &w : workers) w.join();
+    out->push(nullptr);
+}
 
 }  // namespace ingest

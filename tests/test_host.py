@@ -597,6 +597,56 @@ def test_bam_and_sam_ingest_equals_fastq(tmp_path):
         assert digest(write("c.bam", b2), True) == digest(write("c.fq", clean), False) == digest(write("c.sam", s2), True)
 
 
+def test_stream_parallel_parse_equals_single_parser(tmp_path):
+    """TGSF_STREAM_PARSE_THREADS (opt-in, src/pipeline.hpp stream_reader_main): the decoded bytes of gzip / BGZF input
+    are cut into chunks at verified record starts and parsed by several threads; records, order and the behaviour
+    at a malformed record must be those of the single parser thread (FASTQ incl. quality lines starting with '@',
+    2-line FASTA, records longer than a chunk)."""
+    import gzip
+    import subprocess
+    import bam_lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "ingest_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(8)
+    recs, fa = [], []
+    for i in range(900):
+        ln = int(rng.integers(1, 5)) if i % 100 == 3 else int(rng.integers(50, 20000))
+        if i == 450:
+            ln = 400000  # longer than a chunk
+        seq = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), ln).tobytes()
+        q = bytearray(rng.integers(33, 75, ln).astype(np.uint8).tobytes())
+        if i % 7 == 0:
+            q[0] = ord("@")
+        recs.append(b"@r%d some comment\n" % i + seq + b"\n+\n" + bytes(q) + b"\n")
+        fa.append(b">r%d\n" % i + seq + b"\n")
+    fq = b"".join(recs)
+    bad = b"".join(recs[:600]) + b"@broken\nACGT\n+\nII\n" + b"".join(recs[600:])
+
+    def digest(path, fastq, stream, chunk):
+        env = dict(os.environ, INGEST_ONLY="serial", INGEST_HASH="1", TGSF_INFLATE_THREADS="4", TGSF_PINFLATE_MIN_BYTES="100000")
+        if stream:
+            env["TGSF_STREAM_PARSE_THREADS"] = "3"
+        r = subprocess.run([exe, path, "1" if fastq else "0", chunk, "1"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.split()[:3]
+
+    def write(name, blob):
+        path = str(tmp_path / name)
+        with open(path, "wb") as f:
+            f.write(blob)
+        return path
+
+    for name, blob, fastq in (("a.fq.gz", gzip.compress(fq, 4), True), ("b.fq.gz", bam_lib.bgzf(fq), True),
+                              ("c.fa.gz", gzip.compress(b"".join(fa), 4), False), ("d.fq.gz", gzip.compress(bad, 4), True)):
+        path = write(name, blob)
+        for chunk in ("100000", "3000000"):
+            want = digest(path, fastq, False, chunk)
+            assert digest(path, fastq, True, chunk) == want, (name, chunk)
+        assert int(want[0]) == (600 if name == "d.fq.gz" else 900)
+
+
 def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
     """tgsfilter_b200/csrc/gzenc_core.h (code lengths, canonical codes, dynamic block header — the serial half
     of the GPU deflate encoder) built for the host: members assembled from it must inflate with zlib to the
