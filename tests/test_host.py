@@ -647,6 +647,32 @@ def test_stream_parallel_parse_equals_single_parser(tmp_path):
         assert int(want[0]) == (600 if name == "d.fq.gz" else 900)
 
 
+def test_reader_stops_mid_stream_and_restarts(tmp_path):
+    """Two-pass mode of the CLI (pre-pass sample over the buffer budget): the reader thread is stopped after a few
+    batches, drained, joined and started again from the beginning of the file.  With the parallel decoders behind it
+    (single stream, BGZF) the first round must end promptly and the second must deliver the whole file."""
+    import gzip
+    import subprocess
+    import bam_lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "restart_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "restart_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    fq = synth.make_config(2, 400, max_len=30000, with_names=False).to_fastq()
+    n_reads, n_bases = fq.count(b"\n") // 4, sum(len(l) for l in fq.split(b"\n")[1::4])
+    for name, blob in (("a.fq.gz", gzip.compress(fq, 1)), ("b.fq.gz", bam_lib.bgzf(fq))):
+        path = str(tmp_path / name)
+        with open(path, "wb") as f:
+            f.write(blob)
+        for extra in ({}, {"TGSF_STREAM_PARSE_THREADS": "2"}):
+            env = dict(os.environ, TGSF_INFLATE_THREADS="5", TGSF_PINFLATE_MIN_BYTES="100000", **extra)
+            r = subprocess.run([exe, path, "500000", "2"], capture_output=True, text=True, env=env, timeout=120)
+            assert r.returncode == 0, r.stderr
+            rounds = [l.split() for l in r.stdout.splitlines()]
+            assert int(rounds[0][4]) < n_bases and int(rounds[0][-2]) >= 2
+            assert (int(rounds[1][2]), int(rounds[1][4])) == (n_reads, n_bases)
+
+
 def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
     """tgsfilter_b200/csrc/gzenc_core.h (code lengths, canonical codes, dynamic block header — the serial half
     of the GPU deflate encoder) built for the host: members assembled from it must inflate with zlib to the
