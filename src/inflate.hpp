@@ -717,6 +717,27 @@ private:
     std::condition_variable cv_;
 };
 
+// What MultiMemberReader falls back to: by default the streaming GzReader; pinflate.hpp registers a factory that
+// decodes a large remainder with its parallel single-stream reader instead.
+struct TailReader {
+    virtual ~TailReader() {}
+    virtual size_t read(void *dst, size_t n) = 0;
+    virtual bool failed() const = 0;
+    virtual const char *error() const = 0;
+};
+struct GzTail : TailReader {
+    GzReader r;
+    GzTail(const uint8_t *p, size_t n) : r(p, n) {}
+    size_t read(void *dst, size_t n) override { return r.read(dst, n); }
+    bool failed() const override { return r.failed(); }
+    const char *error() const override { return r.error(); }
+};
+typedef TailReader *(*TailFactory)(const uint8_t *data, size_t n, int threads);
+inline TailFactory &tail_factory() {
+    static TailFactory f = nullptr;
+    return f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Concatenated gzip members without block-size headers (`cat *.fastq.gz` of a sequencing run, this
 // tool's own per-record members): member starts are *guessed* by scanning for a plausible gzip header,
@@ -779,10 +800,12 @@ public:
         }
         ok_ = true;
         window_ = (size_t)std::max(4, 2 * threads);
+        threads_ = std::max(1, threads);
         for (int t = 0; t < std::max(1, threads); ++t) workers_.emplace_back([this] { work(); });
     }
     ~MultiMemberReader() {
         shutdown();
+        tail_.reset(); // may run threads over the mapping
         if (base_) munmap((void *)base_, size_);
         if (fd_ >= 0) close(fd_);
     }
@@ -847,7 +870,8 @@ private:
     void fallback() { // sequential decode from the last verified member boundary
         shutdown();
         tasks_.clear();
-        tail_.reset(new GzReader(base_ + expected_, size_ - expected_));
+        TailReader *t = tail_factory() ? tail_factory()(base_ + expected_, size_ - expected_, threads_) : nullptr;
+        tail_.reset(t ? t : new GzTail(base_ + expected_, size_ - expected_));
     }
     Task *next_task() { // m_ held
         if (scan_done_) return nullptr;
@@ -911,7 +935,8 @@ private:
     const char *error_ = nullptr;
     std::deque<std::unique_ptr<Task>> tasks_;
     std::vector<std::thread> workers_;
-    std::unique_ptr<GzReader> tail_;
+    std::unique_ptr<TailReader> tail_;
+    int threads_ = 1;
     std::mutex m_;
     std::condition_variable cv_;
 };

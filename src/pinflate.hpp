@@ -894,4 +894,20 @@ private:
     std::atomic<uint64_t> phase_ns_[3] = {{0}, {0}, {0}};
 };
 
+// MultiMemberReader's fallback (a member too large for one speculative span, a guessed header that was none):
+// a remainder of at least 1 MB that starts with a gzip header is decoded in parallel as well.
+struct ParallelTail : TailReader {
+    SingleStreamReader r;
+    ParallelTail(const uint8_t *p, size_t n, int threads) : r(p, n, threads, 0) {}
+    size_t read(void *dst, size_t n) override { return r.read(dst, n); }
+    bool failed() const override { return r.failed(); }
+    const char *error() const override { return r.error(); }
+};
+namespace pinf {
+static const bool tail_registered = (tail_factory() = [](const uint8_t *p, size_t n, int threads) -> TailReader * {
+    if (threads < 2 || n < (1u << 20) || !gzip_header_len(p, n) || getenv("TGSF_SERIAL_INFLATE")) return nullptr;
+    return new ParallelTail(p, n, threads);
+}, true);
+}
+
 }  // namespace fastgz

@@ -673,6 +673,39 @@ def test_reader_stops_mid_stream_and_restarts(tmp_path):
             assert (int(rounds[1][2]), int(rounds[1][4])) == (n_reads, n_bases)
 
 
+def test_multi_member_fallback_decodes_the_rest_in_parallel(tmp_path):
+    """When MultiMemberReader's chain of guessed member starts breaks (here: a gzip-header-like byte string inside a
+    stored block) the remainder goes to the parallel single-stream reader (src/pinflate.hpp registers itself as the
+    fallback) instead of the streaming decoder: the records must equal those of the sequential decoder and of zlib."""
+    import gzip
+    import subprocess
+    import zlib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "ingest_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
+                    "-lz", "-o", exe], check=True)
+    rng = np.random.default_rng(12)
+    recs = [b"@r%d\n" % i + rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 20000).tobytes() + b"\n+\n" +
+            rng.integers(33, 75, 20000).astype(np.uint8).tobytes() + b"\n" for i in range(900)]
+    fake = b"@x \x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03 y\nACGT\n+\nIIII\n"
+    c = zlib.compressobj(0, zlib.DEFLATED, 31)  # stored blocks keep the fake header verbatim
+    m1 = c.compress(b"".join(recs[:250]) + fake + b"".join(recs[250:300])) + c.flush()
+    blob = m1 + gzip.compress(b"".join(recs[300:600]), 1) + gzip.compress(b"".join(recs[600:]), 1)
+    path = str(tmp_path / "mm.fq.gz")
+    with open(path, "wb") as f:
+        f.write(blob)
+
+    def digest(**extra):
+        env = dict(os.environ, INGEST_ONLY="serial", INGEST_HASH="1", TGSF_INFLATE_THREADS="5", **extra)
+        r = subprocess.run([exe, path, "1", "3000000", "1"], capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        return r.stdout.split()[:3]
+
+    want = digest(TGSF_ZLIB_INFLATE="1")
+    assert want[0] == "901"
+    assert digest() == want and digest(TGSF_SERIAL_INFLATE="1") == want and digest(TGSF_STREAM_PARSE_THREADS="2") == want
+
+
 def test_gzip_member_format_of_the_gpu_encoder_on_cpu(tmp_path):
     """tgsfilter_b200/csrc/gzenc_core.h (code lengths, canonical codes, dynamic block header — the serial half
     of the GPU deflate encoder) built for the host: members assembled from it must inflate with zlib to the
