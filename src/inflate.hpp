@@ -898,13 +898,23 @@ private:
                 t = next_task();
                 if (!t) { cv_.notify_all(); return; }
             }
+            if (tail_factory() && t->stop - t->start > 3 * (size_t)SPAN) {
+                // no member start for 24 MB: a member this large goes to the parallel single-stream decoder undecoded
+                std::lock_guard<std::mutex> lk(m_);
+                t->too_big = true;
+                t->end = t->start;
+                t->state = 2;
+                cv_.notify_all();
+                continue;
+            }
             rd.reset(base_ + t->start, size_ - t->start);
             rd.set_stop(t->stop - t->start);
             t->out.resize(std::min<size_t>(4 * (t->stop - t->start) + (1u << 20), 64u << 20));
             size_t got = 0;
             while (true) {
                 if (got == t->out.size()) {
-                    if (got >= SPAN_OUT_CAP) { t->too_big = true; break; }
+                    // with the parallel single-stream decoder as fallback a member beyond 64 MB is better decoded there
+                    if (got >= (tail_factory() ? (size_t)(64u << 20) : (size_t)SPAN_OUT_CAP)) { t->too_big = true; break; }
                     t->out.resize(got * 2);
                 }
                 const size_t k = rd.read(t->out.data() + got, t->out.size() - got);
