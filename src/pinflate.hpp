@@ -452,6 +452,8 @@ public:
     const char *error() const { return error_; }
     size_t repairs() const { return repairs_ + (next_ ? next_->repairs() : 0); } // spans decoded a second time (tests, diagnostics)
     size_t spans() const { return nspans_ + (next_ ? next_->spans() : 0); }
+    // spans accepted as decoded speculatively, i.e. against an unknown window (tests, diagnostics)
+    size_t speculated() const { return speculated_ + (next_ ? next_->speculated() : 0); }
     // worker seconds spent in block search / symbolic decode / placeholder resolution + CRC (diagnostics)
     void phase_seconds(double out[3]) const { for (int i = 0; i < 3; ++i) out[i] = phase_ns_[i].load() * 1e-9; }
 
@@ -722,6 +724,7 @@ private:
                 return;
             }
             if (t.idx > 0 && !t.known_start) consecutive_repairs_ = 0;
+            if (!t.direct) ++speculated_;
             t.win = chain_window_;
             t.win_valid = chain_valid_;
             // the window behind this span: last HIST bytes of (window | resolved symbols)
@@ -875,7 +878,7 @@ private:
     std::atomic<unsigned> not_found_{0};
     std::unique_ptr<std::atomic<uint64_t>[]> found_;
     const char *error_ = nullptr;
-    size_t next_idx_ = 0, front_idx_ = 0, chain_next_ = 0, repairs_ = 0, consecutive_repairs_ = 0;
+    size_t next_idx_ = 0, front_idx_ = 0, chain_next_ = 0, repairs_ = 0, consecutive_repairs_ = 0, speculated_ = 0;
     uint64_t chain_end_bit_ = 0;
     std::vector<uint8_t> chain_window_;
     size_t chain_valid_ = 0;

@@ -26,7 +26,7 @@ int main(int argc, char **argv) {
         if (fail_a) fprintf(stderr, "serial: %s\n", r.error());
     }
     auto t1 = std::chrono::steady_clock::now();
-    size_t spans = 0, repairs = 0;
+    size_t spans = 0, repairs = 0, speculated = 0;
     {
         fastgz::SingleStreamReader r(argv[1], atoi(argv[2]), span);
         if (!r.ok()) return 3;
@@ -36,14 +36,15 @@ int main(int argc, char **argv) {
         if (fail_b) fprintf(stderr, "parallel: %s\n", r.error());
         spans = r.spans();
         repairs = r.repairs();
+        speculated = r.speculated();
         double ph[3];
         r.phase_seconds(ph);
         fprintf(stderr, "worker seconds: search %.3f decode %.3f resolve+crc %.3f\n", ph[0], ph[1], ph[2]);
     }
     auto t2 = std::chrono::steady_clock::now();
     const double da = std::chrono::duration<double>(t1 - t0).count(), db = std::chrono::duration<double>(t2 - t1).count();
-    printf("%zu %zu fail %d %d  serial %.0f MB/s  parallel %.0f MB/s  spans %zu repairs %zu\n", a.size(), b.size(), (int)fail_a,
-           (int)fail_b, a.size() / da / 1e6, b.size() / db / 1e6, spans, repairs);
+    printf("%zu %zu fail %d %d  serial %.0f MB/s  parallel %.0f MB/s  speculated %zu spans %zu repairs %zu\n", a.size(), b.size(), (int)fail_a,
+           (int)fail_b, a.size() / da / 1e6, b.size() / db / 1e6, speculated, spans, repairs);
     if (fail_a != fail_b) return 1;
     if (fail_a) return (b.size() <= a.size() + (4u << 20) && std::equal(b.begin(), b.begin() + std::min(a.size(), b.size()), a.begin())) ? 0 : 1;
     return (a == b) ? 0 : 1;

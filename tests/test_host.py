@@ -489,7 +489,7 @@ def test_parallel_single_stream_inflate_equals_sequential_decode(tmp_path):
             assert r.returncode == 0, (what, t, r.stdout, r.stderr)
             w = r.stdout.split()
             assert (int(w[3]), int(w[4])) == (failed, failed), (what, t, r.stdout)
-            res = dict(size=int(w[1]), spans=int(w[-3]), repairs=int(w[-1]))
+            res = dict(size=int(w[1]), speculated=int(w[-5]), spans=int(w[-3]), repairs=int(w[-1]))
         return res
 
     for name, d in datasets.items():
@@ -507,6 +507,7 @@ def test_parallel_single_stream_inflate_equals_sequential_decode(tmp_path):
             if name == "fastq" and vn in ("l1", "l6", "l9", "huff", "sync", "full"):
                 # text in dynamic blocks: the search lines the spans up (a flush's empty stored block is decoded through)
                 assert r["spans"] > 20 and r["repairs"] <= r["spans"] // 10, (vn, r)
+                assert r["speculated"] >= r["spans"] // 2, (vn, r)  # decoded against the unknown window, not one by one
     # memory bound: a span that expands beyond the soft cap is closed at a block boundary and the spans behind it
     # are decoded from there in turn, the last one as often as it takes (TGSF_PINFLATE_SOFT_CAP is a test knob)
     os.environ["TGSF_PINFLATE_SOFT_CAP"] = "50000"
