@@ -530,7 +530,7 @@ def test_parallel_single_stream_inflate_equals_sequential_decode(tmp_path):
     run(bytes(z), "default and oversized span", threads=("4",), span="16777216")
 
 
-def test_bam_and_sam_ingest_equals_fastq(tmp_path):
+def test_bam_and_sam_ingest_equals_fastq(tmp_path, cpp_tool):
     """BAM / SAM input (read_bam, T.cpp:1872-1916) is parsed by src/pipeline.hpp without htslib: the records must
     equal those of the equivalent FASTQ — every record whatever its flags, bases through the reference's nibble
     table (lower case folded, ambiguity codes and '=' -> NUL, unknown -> N), quality + 33 (absent: 0xFF + 33 = ' '),
@@ -539,9 +539,7 @@ def test_bam_and_sam_ingest_equals_fastq(tmp_path):
     import subprocess
     import bam_lib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "ingest_check")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
-                    "-lz", "-o", exe], check=True)
+    exe = cpp_tool("ingest_check")
     rng = np.random.default_rng(3)
 
     def digest(path, sambam, threads="4", chunk="3000000"):
@@ -598,7 +596,7 @@ def test_bam_and_sam_ingest_equals_fastq(tmp_path):
         assert digest(write("c.bam", b2), True) == digest(write("c.fq", clean), False) == digest(write("c.sam", s2), True)
 
 
-def test_stream_parallel_parse_equals_single_parser(tmp_path):
+def test_stream_parallel_parse_equals_single_parser(tmp_path, cpp_tool):
     """TGSF_STREAM_PARSE_THREADS (opt-in, src/pipeline.hpp stream_reader_main): the decoded bytes of gzip / BGZF input
     are cut into chunks at verified record starts and parsed by several threads; records, order and the behaviour
     at a malformed record must be those of the single parser thread (FASTQ incl. quality lines starting with '@',
@@ -607,9 +605,7 @@ def test_stream_parallel_parse_equals_single_parser(tmp_path):
     import subprocess
     import bam_lib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "ingest_check")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
-                    "-lz", "-o", exe], check=True)
+    exe = cpp_tool("ingest_check")
     rng = np.random.default_rng(8)
     recs, fa = [], []
     for i in range(900):
@@ -674,7 +670,7 @@ def test_reader_stops_mid_stream_and_restarts(tmp_path):
             assert (int(rounds[1][2]), int(rounds[1][4])) == (n_reads, n_bases)
 
 
-def test_multi_member_fallback_decodes_the_rest_in_parallel(tmp_path):
+def test_multi_member_fallback_decodes_the_rest_in_parallel(tmp_path, cpp_tool):
     """When MultiMemberReader's chain of guessed member starts breaks (here: a gzip-header-like byte string inside a
     stored block) the remainder goes to the parallel single-stream reader (src/pinflate.hpp registers itself as the
     fallback) instead of the streaming decoder: the records must equal those of the sequential decoder and of zlib."""
@@ -682,9 +678,7 @@ def test_multi_member_fallback_decodes_the_rest_in_parallel(tmp_path):
     import subprocess
     import zlib
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    exe = str(tmp_path / "ingest_check")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", os.path.join(root, "tests", "cpp", "ingest_check.cpp"),
-                    "-lz", "-o", exe], check=True)
+    exe = cpp_tool("ingest_check")
     rng = np.random.default_rng(12)
     recs = [b"@r%d\n" % i + rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), 20000).tobytes() + b"\n+\n" +
             rng.integers(33, 75, 20000).astype(np.uint8).tobytes() + b"\n" for i in range(900)]
