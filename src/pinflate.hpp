@@ -21,7 +21,7 @@
 //      the consumer combines the CRCs (crc32_combine) and checks the member trailer.
 // A large member behind this one (`cat a.fq.gz b.fq.gz`) gets a reader of its own; small remainders and
 // padding go to the streaming GzReader.
-// tests/cpp/pinflate_check.cpp pins it against the sequential GzReader and zlib.
+// tests/cpp/pinflate_check.cpp pins it against the sequential GzReader (itself pinned against zlib by inflate_check.cpp).
 #pragma once
 #include "inflate.hpp"
 
