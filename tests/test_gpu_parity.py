@@ -614,9 +614,9 @@ def _repeat_batch(seed, n=48, long_read=0):
         if i % 3 == 0:
             s[rng.integers(0, L, max(1, L // 40))] = np.frombuffer(b"Nacgt", dtype=np.uint8)[rng.integers(0, 5, max(1, L // 40))]
         seqs.append(s.tobytes())
-    if long_read:
+    for j, lr in enumerate(long_read if isinstance(long_read, (list, tuple)) else ([long_read] if long_read else [])):
         unit = acgt[rng.integers(0, 4, 70001)]
-        seqs.insert(3, np.concatenate([np.tile(unit, long_read // 70001 + 1)[:long_read]]).tobytes())
+        seqs.insert(3 + 2 * j, np.concatenate([np.tile(unit, lr // 70001 + 1)[:lr]]).tobytes())
     quals = [bytes([40 + 33]) * len(s) for s in seqs]
     return synth.pack_reads(seqs, quals)
 
@@ -626,12 +626,20 @@ def test_kmer_repeat_length_on_every_kernel_path(k, monkeypatch):
     """GetKmerCount (T.cpp:1703-1753): k <= 12: tag rounds (piece fits one staged tile) or shared-memory
     bitmap passes (longer pieces); global bitmap (13), hash sets (> 13); -p drops pieces whose repeat
     length is below the bound."""
-    batch = _repeat_batch(100 + k, long_read=450000 if k in (5, 11, 12) else 0)
+    # long reads: one pass / two passes / four passes of k_kmer_tag16, just above its 16-bit position range, and
+    # several staged tiles of k_kmer_smem
+    batch = _repeat_batch(100 + k, long_read=[450000, 19000, 33000, 64990, 65100] if k in (5, 11, 12) else 0)
     params = FilterParams(min_len=50, min_q=0.0, kmer=k, min_repeat=200, qtype=33, adapters=[],
                           max_read_len=500000)
     r, p, _ = _compare(params, batch)
     assert (p["status"] != 0).any() and (p["status"] == 0).any()
     if k in (8, 11, 12):  # the other kernels for the same k on the same input
+        monkeypatch.setenv("TGSF_KMER16_LIST_CAP", "64")  # nearly every pass overflows the pending list: retry path
+        _compare(params, batch)
+        monkeypatch.delenv("TGSF_KMER16_LIST_CAP")
+        monkeypatch.setenv("TGSF_KMER_TAG32", "1")
+        _compare(params, batch)
+        monkeypatch.delenv("TGSF_KMER_TAG32")
         monkeypatch.setenv("TGSF_KMER_BITMAP", "1")
         _compare(params, batch)
         monkeypatch.delenv("TGSF_KMER_BITMAP")

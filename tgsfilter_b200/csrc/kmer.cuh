@@ -408,7 +408,8 @@ static __device__ u32 kmer_tag_count(const u32 *tile, u32 *table, uint16_t *pend
 
 __global__ void __launch_bounds__(KMER_SB_THREADS, 1)
 k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pieces_ptr,
-            u64 *__restrict__ counters, const u32 *__restrict__ dev_status, int force_bitmap) {
+            u64 *__restrict__ counters, const u32 *__restrict__ dev_status, int force_bitmap,
+            const u32 *__restrict__ piece_list) { // piece_list != null: n_pieces_ptr counts its entries (the pieces k_kmer_tag16 left)
     if (*dev_status != DEV_STATUS_OK) return;
     extern __shared__ __align__(16) uint8_t kmem[];
     u32 *bm = (u32 *)kmem;
@@ -423,7 +424,8 @@ k_kmer_smem(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__
     const u64 n_total = B.offsets[B.n_reads];
     const u32 tile_kmers = KMER_SB_TILE_WORDS * 16 - 16 - (u32)(k - 1); // k-mers one staged tile can hold (15 bases of slack for the alignment shift)
 
-    for (u32 pi = blockIdx.x; pi < n_pieces; pi += gridDim.x) {
+    for (u32 li = blockIdx.x; li < n_pieces; li += gridDim.x) {
+        const u32 pi = piece_list ? piece_list[li] : li;
         tgsf_piece pc = pieces[pi];
         if (pc.status != TGSF_PIECE_EMIT) continue;
         const int total = pc.len - k + 1;

@@ -3,7 +3,7 @@
 // Replaces include/edlib.cpp's calculateBlock (E.cpp:409-444), myersCalcEditDistanceSemiGlobal
 // (E.cpp:547-704, HW and SHW modes), myersCalcEditDistanceNW (E.cpp:730-931) and
 // obtainAlignmentTraceback (E.cpp:945-1144) with the equivalent specification validated in
-// SURVEY.md §3.5 / tests/test_oracle_vs_ref.py: plain semi-global DP semantics, all end columns
+// SURVEY.md §3.5 / tests/test_oracle.py: plain semi-global DP semantics, all end columns
 // with the best distance, smallest start per end, traceback priority Up > Left > Diagonal.
 //
 // Layouts.  HW scans use a TOP-padded pattern: the 64*NW-bit column holds W = 64*NW - q wildcard

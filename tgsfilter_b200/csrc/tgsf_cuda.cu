@@ -15,6 +15,7 @@
 #include "adapters.cuh"
 #include "common.cuh"
 #include "kmer.cuh"
+#include "kmer16.cuh"
 #include "gzenc.cuh"
 #include "prepass.cuh"
 #include "regions.cuh"
@@ -184,6 +185,8 @@ struct DevHeader { // small block mirrored to the host with every batch
     u32 sort_cursor;
     u32 gz_overflow; // k_gz_encode ran out of blob space
     unsigned long long gz_cursor; // bytes of deflate blocks produced
+    u32 kmer_work;   // k_kmer_tag16: next piece to take
+    u32 kmer_long;   // pieces it left for k_kmer_smem (too long for 16-bit positions)
 };
 
 struct Slot {
@@ -201,7 +204,7 @@ struct Slot {
     DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first, chunk_perm, chunk_hist;
     int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
-    DBuf scan_tmp, kmer_bitmaps, gz_blob, gz_spans;
+    DBuf scan_tmp, kmer_bitmaps, kmer_long_list, gz_blob, gz_spans;
     Scratch scratch;
     u32 pool_cap = 0, pieces_cap = 0, chunks_cap = 0, tiles_cap = 0;
     // host results
@@ -223,6 +226,9 @@ struct tgsf_ctx {
     u64 launches = 0;
     bool kmer_force_l2 = false; // TGSF_KMER_L2=1: keep k <= 12 on the global-memory bitmap kernel (A/B, tests)
     bool kmer_force_bitmap = false; // TGSF_KMER_BITMAP=1: shared-memory bitmap passes also for single-tile pieces
+    bool kmer_force_tag32 = false;  // TGSF_KMER_TAG32=1: k <= 12 stays on k_kmer_smem alone (round-1 kernel; A/B, tests)
+    int kmer16_ctas_per_sm = 2;
+    u32 kmer16_list_cap = KMER16_LIST_CAP; // TGSF_KMER16_LIST_CAP=n: smaller pending list (tests of the retry path)
     float last_kernel_ms = 0, last_total_ms = 0;
     float last_stage_ms[TGSF_N_STAGES] = {};
 };
@@ -269,7 +275,7 @@ void slot_release(Slot &s) {
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
                     &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
-                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.gz_blob, &s.gz_spans, &s.scratch.buf};
+                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.kmer_long_list, &s.gz_blob, &s.gz_spans, &s.scratch.buf};
     for (DBuf *b : bufs) b->release();
     s.h_res.release();
     s.h_pieces.release();
@@ -576,10 +582,21 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
     c->launches++;
     CU(cudaEventRecord(s.ev_stage[5], st));
     if (!(P.flags & TGSF_FLAG_ONLY_QC)) {
-        if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2) {
-            // shared-memory bitmap in key-range passes
+        if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2 && !c->kmer_force_bitmap && !c->kmer_force_tag32) {
+            // 16-bit position tags, two CTAs per SM; pieces too long for 16-bit positions go to k_kmer_smem
+            TRY(s.kmer_long_list.ensure((size_t)s.pieces_cap * sizeof(u32)));
+            k_kmer_tag16<<<c->sm_count * c->kmer16_ctas_per_sm, KMER16_THREADS, KMER16_SMEM_BYTES, st>>>(
+                s.B, P, s.pieces.as<tgsf_piece>(), &H->tmp_cursor, C, &H->status, &H->kmer_work,
+                s.kmer_long_list.as<u32>(), &H->kmer_long, c->kmer16_list_cap);
             k_kmer_smem<<<c->sm_count, KMER_SB_THREADS, KMER_SB_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
-                                                                                 &H->tmp_cursor, C, &H->status, c->kmer_force_bitmap ? 1 : 0);
+                                                                                 &H->kmer_long, C, &H->status, 0,
+                                                                                 s.kmer_long_list.as<u32>());
+            c->launches += 2;
+        } else if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2) {
+            // round-1 path: 32-bit tag rounds / shared-memory bitmap in key-range passes, one CTA per SM
+            k_kmer_smem<<<c->sm_count, KMER_SB_THREADS, KMER_SB_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
+                                                                                 &H->tmp_cursor, C, &H->status, c->kmer_force_bitmap ? 1 : 0,
+                                                                                 nullptr);
             c->launches++;
         } else if (P.min_repeat > 0 && P.kmer <= 13) {
             // bitmap path: one 4^k-bit map per CTA, zeroed once and kept clean by the kernel
@@ -758,9 +775,17 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
         cudaError_t e2 = cudaFuncSetAttribute(k_scan_tiles_dyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
         c->kmer_force_l2 = getenv("TGSF_KMER_L2") != nullptr;
         c->kmer_force_bitmap = getenv("TGSF_KMER_BITMAP") != nullptr;
+        c->kmer_force_tag32 = getenv("TGSF_KMER_TAG32") != nullptr;
+        if (const char *e = getenv("TGSF_KMER16_LIST_CAP")) c->kmer16_list_cap = (u32)std::min<long>(std::max<long>(atol(e), 32), (long)KMER16_LIST_CAP);
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         if (e4 == cudaSuccess) e4 = cudaFuncSetAttribute(k_kmer_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SB_SMEM_BYTES);
+        if (e3 == cudaSuccess) e3 = cudaFuncSetAttribute(k_kmer_tag16, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER16_SMEM_BYTES);
+        if (e3 == cudaSuccess) {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_kmer_tag16, KMER16_THREADS, KMER16_SMEM_BYTES) == cudaSuccess && occ >= 1)
+                c->kmer16_ctas_per_sm = occ;
+        }
         if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
             set_err("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3 != cudaSuccess ? e3 : e4));
             rc = TGSF_ERR_CUDA;
