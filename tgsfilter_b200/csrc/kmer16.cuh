@@ -1,36 +1,50 @@
-// K4, k <= 12, pieces of up to KMER16_MAX_KMERS k-mers: distinct k-mer count with 16-bit "last writer
-// wins" position tags.  Replaces GetKmerCount (T.cpp:1703-1753) for the common case (the default k = 11
-// on HiFi / CLR / ordinary ONT pieces); longer pieces are handed to k_kmer_smem through a device list.
+// K4, k <= 12, pieces of up to KMER16_MAX_KMERS k-mers: distinct k-mer count without shared-memory
+// atomics on the k-mer path.  Replaces GetKmerCount (T.cpp:1703-1753) for the common case (the default
+// k = 11 on HiFi / CLR / ordinary ONT pieces); longer pieces are handed to k_kmer_smem through a device
+// list.  Two CTAs per SM; inside a CTA two PRODUCER warps stage the next two pieces (global loads, ASCII
+// -> 2-bit codes, one tile buffer each) while 14 CONSUMER warps count the current one, so neither the
+// global-load latency nor the piece metadata chain is ever on the consumers' path (named barriers:
+// consumers among themselves, full / empty per tile buffer).
 //
-// Same idea as the 32-bit tag rounds of k_kmer_smem (no shared-memory atomics on the k-mer path: every
-// pending k-mer stores a tag into the slot its key hashes to, and after one barrier reads the slot
-// back), re-cut so that TWO CTAs fit one SM and overlap each other's barriers and global-load latency:
-//   * the tag is the k-mer's POSITION only (u16), so 32 768 slots cost 64 KB instead of 128 KB.  A
-//     k-mer that reads back its own position is the one representative of its key (count 1); otherwise
-//     it fetches the winner's key from the staged 2-bit stream and compares: equal -> duplicate of the
-//     representative, different -> its key lost the slot and stays pending.  All instances of a key
-//     share slot and winner, so keys are resolved as a whole, and a k-mer only reads a slot it wrote in
-//     the same round, so the table is never cleared.
-//   * one dense round per pass (slot = low 15 bits of the key), the losers go straight to a position
-//     list (warp-aggregated append, one shared atomic per warp) and are resolved by list rounds with a
-//     multiplicative hash; the last <= 32 keys are settled by one warp with __match_any_sync.
+// Counting a staged piece (k16_count):
+//   * dense round, "owner bytes": the table is 65 536 BYTE slots.  slot = top 16 bits of the key, and
+//     every k-mer stores (low key bits | 0x80) there — no position, no atomics, last writer wins.  After
+//     one barrier a k-mer that reads back its own byte belongs to the key that owns the slot; all
+//     instances of a key share slot and verdict, so the keys resolved by the round are exactly the
+//     non-empty slots, counted by one sweep over the table, and no lane ever branches on table contents.
+//     The k-mers of every other key are appended to a pending list (warp-aggregated, one shared atomic
+//     per warp and word).
+//   * list rounds: the same memory as 32 768 u16 position tags, slot = multiplicative hash of the key.
+//     A pending k-mer that reads back its own position is the representative of its key (count 1);
+//     otherwise it fetches the winner's key from the staged stream: equal -> duplicate, different -> it
+//     lost again and goes to the next list.  A k-mer only reads a slot it wrote in the same round.  The
+//     last <= 32 keys are settled by one warp with __match_any_sync.
 //   * pieces with more than KMER16_ONE_PASS k-mers are processed in 2^n passes over the classes given by
-//     the TOP bits of the key, so the table load stays <= ~0.6.  If a pass still produces more losers
-//     than the list holds, the piece is redone with twice the passes; with one class per remainder value
-//     no slot can hold two keys, so the retry loop always terminates.
+//     the top bits of the key REMAINDER (the bits that are not in the slot), so the table load stays
+//     <= 0.4.  If a pass still produces more losers than the list holds, the piece is redone with twice
+//     the passes; with one class per remainder value no slot can hold two keys, so this terminates.
 // Base codes: (byte >> 1) & 3 (A0 C1 T2 G3) — any injective recoding of ACGT counts the same distinct
 // k-mers as the reference's A0 C1 G2 T3; every other byte must collide with 'A' (T.cpp:1709-1724) and
 // is recoded to 0 on a slow path that only runs for 16-byte groups containing such a byte.
 #pragma once
 #include "common.cuh"
 
-#define KMER16_THREADS 512
-#define KMER16_SLOTS 32768u
+#define KMER16_CONSUMERS 448                         // 14 warps count
+#define KMER16_THREADS 512                           // + 2 warps that stage the next two pieces (one tile buffer each)
+#define KMER16_TABLE_BYTES 65536u                    // 65 536 owner bytes / 32 768 u16 position tags
 #define KMER16_TILE_WORDS 4096u                      // 16 bases per word
-#define KMER16_MAX_KMERS 65000u                      // positions (alignment shift included) fit u16
-#define KMER16_LIST_CAP 6144u
-#define KMER16_ONE_PASS 20000u
-#define KMER16_SMEM_BYTES (KMER16_SLOTS * 2u + (KMER16_TILE_WORDS + 2u) * 4u + 2u * KMER16_LIST_CAP * 2u)
+#define KMER16_MAX_KMERS 65000u                      // one staged tile; positions (alignment shift included) fit u16
+#define KMER16_LIST_CAP 4096u
+#define KMER16_ONE_PASS 22000u                       // table load 0.34: ~15 % of the k-mers lose their slot
+#define KMER16_TILE_BYTES ((KMER16_TILE_WORDS + 2u) * 4u)
+#define KMER16_SMEM_BYTES (KMER16_TABLE_BYTES + 2u * KMER16_TILE_BYTES + 2u * KMER16_LIST_CAP * 2u)
+#define KMER16_END 0xFFFFFFFFu
+
+struct K16Meta { u32 pi, shift; int total, len; };
+
+static __device__ __forceinline__ void k16_bar_sync(u32 id, u32 n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+static __device__ __forceinline__ void k16_bar_arrive(u32 id, u32 n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+static __device__ __forceinline__ void k16_sync_consumers() { asm volatile("bar.sync 1, 448;" ::: "memory"); }
 
 // 4 ASCII bases (lowest address in the low byte) -> 8 bits of codes, first base in the top 2 bits;
 // bad |= non-zero iff a byte is not one of A C G T.
@@ -54,27 +68,45 @@ static __device__ __forceinline__ u32 k16_codes4_slow(u32 v) {
     return out;
 }
 
-static __device__ __forceinline__ void k16_stage(const DevBatch &B, u64 n_total, u64 abase, u32 n_words, u32 *tile) {
-    for (u32 w = threadIdx.x; w < n_words + 2; w += KMER16_THREADS) {
-        u32 out = 0;
-        if (w < n_words) {
-            const u64 a = abase + 16ull * w;
-            uint4 q;
-            if (a + 16 <= n_total) {
-                q = __ldg((const uint4 *)(B.bases + a));
-            } else { // last, partial group of the batch: bytes beyond the stream are not touched
-                __align__(16) uint8_t tmp[16];
+static __device__ __forceinline__ u32 k16_codes16(uint4 q) {
+    u32 bad = 0;
+    const u32 c0 = k16_codes4(q.x, bad), c1 = k16_codes4(q.y, bad), c2 = k16_codes4(q.z, bad), c3 = k16_codes4(q.w, bad);
+    u32 out = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    if (bad) out = (k16_codes4_slow(q.x) << 24) | (k16_codes4_slow(q.y) << 16) | (k16_codes4_slow(q.z) << 8) | k16_codes4_slow(q.w);
+    return out;
+}
+
+// Producer warp: bases [abase, abase + 16 * n_words) as 2-bit codes into tile[0 .. n_words), then two zero
+// words (the window of the last k-mer reads past the stream).  Eight 16-byte loads in flight per lane.
+static __device__ __forceinline__ void k16_stage(const DevBatch &B, u64 n_total, u64 abase, u32 n_words, u32 *tile, u32 lane) {
+    const u32 n_full = (abase + 16ull * n_words <= n_total) ? n_words : (u32)((n_total - abase) / 16ull); // words fully inside the stream
+    u32 w = lane;
+    for (; w + 224u < n_full; w += 256u) {
+        uint4 q[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) tmp[j] = (a + j < n_total) ? B.bases[a + j] : (uint8_t)'A';
-                q = *(uint4 *)tmp;
-            }
-            u32 bad = 0;
-            const u32 c0 = k16_codes4(q.x, bad), c1 = k16_codes4(q.y, bad), c2 = k16_codes4(q.z, bad), c3 = k16_codes4(q.w, bad);
-            out = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
-            if (bad)
-                out = (k16_codes4_slow(q.x) << 24) | (k16_codes4_slow(q.y) << 16) | (k16_codes4_slow(q.z) << 8) | k16_codes4_slow(q.w);
+        for (u32 i = 0; i < 8; ++i) q[i] = __ldg((const uint4 *)(B.bases + abase + 16ull * (w + 32u * i)));
+#pragma unroll
+        for (u32 i = 0; i < 8; ++i) tile[w + 32u * i] = k16_codes16(q[i]);
+    }
+    for (; w + 96u < n_full; w += 128u) {
+        uint4 q[4];
+#pragma unroll
+        for (u32 i = 0; i < 4; ++i) q[i] = __ldg((const uint4 *)(B.bases + abase + 16ull * (w + 32u * i)));
+#pragma unroll
+        for (u32 i = 0; i < 4; ++i) tile[w + 32u * i] = k16_codes16(q[i]);
+    }
+    for (; w < n_words + 2u; w += 32u) {
+        u32 out = 0;
+        if (w < n_full) {
+            out = k16_codes16(__ldg((const uint4 *)(B.bases + abase + 16ull * w)));
+        } else if (w < n_words) { // last, partial group of the batch: bytes beyond the stream are not touched
+            __align__(16) uint8_t tmp[16];
+            const u64 a = abase + 16ull * w;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) tmp[j] = (a + j < n_total) ? B.bases[a + j] : (uint8_t)'A';
+            out = k16_codes16(*(uint4 *)tmp);
         }
-        tile[w] = out; // two zero words behind the stream: the window of the last k-mer reads past it
+        tile[w] = out;
     }
 }
 
@@ -83,8 +115,8 @@ static __device__ __forceinline__ u32 k16_kmer_at(const u32 *tile, u32 pos) { //
     return __funnelshift_l(tile[w + 1], tile[w], 2u * (pos & 15u));
 }
 
-// Warp-aggregated append of the positions (pw | j) for the set bits j of `m` to list[*cnt ...] (entries
-// beyond the capacity are dropped; the caller sees the overflow in *cnt).  All 32 lanes must call.
+// Warp-aggregated append of the positions (pw | j) for the set bits j of `m` to list[*cnt ...] (a warp
+// whose entries do not all fit drops them; the caller sees the overflow in *cnt).  All 32 lanes must call.
 static __device__ __forceinline__ void k16_append(u32 m, u32 pw, uint16_t *list, u32 *cnt, u32 lane, u32 list_cap) {
     const u32 c = __popc(m);
     u32 incl = c;
@@ -99,35 +131,43 @@ static __device__ __forceinline__ void k16_append(u32 m, u32 pw, uint16_t *list,
     if (lane == 31) base = atomicAdd(cnt, wtot);
     base = __shfl_sync(0xffffffffu, base, 31);
     u32 off = base + incl - c;
-    while (m) {
-        const u32 j = (u32)__ffs((int)m) - 1u;
-        m &= m - 1u;
-        if (off < list_cap) list[off] = (uint16_t)(pw + j);
-        ++off;
+    if (base + wtot <= list_cap) {
+        while (m) {
+            const u32 j = (u32)__ffs((int)m) - 1u;
+            m &= m - 1u;
+            list[off++] = (uint16_t)(pw + j);
+        }
     }
 }
 
-// One attempt at a staged piece with 2^pass_bits key classes.  Returns false (in every thread) if a pass
-// produced more pending k-mers than the list holds; `mine` then holds garbage and the caller retries.
-static __device__ bool k16_count(const u32 *tile, uint16_t *table, uint16_t *list_a, uint16_t *list_b, u32 *s_cnt,
-                                 u32 shift, u32 p_end, int k, u32 pass_bits, u32 list_cap, u32 &mine) {
-    const u32 sh = 32u - 2u * (u32)k;      // x >> sh = key
-    const u32 n_scan = (p_end + 15u) >> 4; // words holding the start of at least one k-mer
+// One attempt at a staged piece with 2^pass_bits key classes (consumer threads only).  Returns false (in
+// every thread) if a pass produced more pending k-mers than the list holds; the caller retries with more
+// passes.  KT: compile-time k (0: use krt).
+template <int KT>
+static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *list_a, uint16_t *list_b, u32 *s_cnt,
+                                 u32 shift, u32 p_end, int krt, u32 pass_bits, u32 list_cap, u32 &mine) {
+    const int k = KT ? KT : krt;
+    uint16_t *table = (uint16_t *)table8;
+    const u32 sh = 32u - 2u * (u32)k;            // x >> sh = key
+    const u32 slot_sh = sh > 16u ? sh : 16u;     // slot = top 16 bits of the key (the whole key when 2k <= 16)
+    const u32 n_scan = (p_end + 15u) >> 4;       // words holding the start of at least one k-mer
     const u32 lane = threadIdx.x & 31u;
     const u32 n_pass = 1u << pass_bits;
-    const u32 cls_sh = 32u - pass_bits;    // class = top pass_bits bits of the key (pass_bits <= 2k - 15 when it matters)
+    const u32 cls_sh = 16u - pass_bits;          // class = top pass_bits bits of the remainder x[15 : sh]
     mine = 0;
     for (u32 pass = 0; pass < n_pass; ++pass) {
-        __syncthreads(); // previous pass / piece is done with the table, the lists and s_cnt
+        k16_sync_consumers(); // previous pass / piece is done with the table, the lists and s_cnt
         if (threadIdx.x == 0) { s_cnt[0] = 0; s_cnt[1] = 0; }
-        // ---- dense round, store: slot = low 15 bits of the key ----
-        for (u32 w = threadIdx.x; w < n_scan; w += KMER16_THREADS) {
+        for (u32 i = threadIdx.x; i < KMER16_TABLE_BYTES / 16u; i += KMER16_CONSUMERS) ((uint4 *)table8)[i] = make_uint4(0, 0, 0, 0);
+        k16_sync_consumers();
+        // ---- dense round, store ----
+        for (u32 w = threadIdx.x; w < n_scan; w += KMER16_CONSUMERS) {
             const u32 w0 = tile[w], w1 = tile[w + 1], pw = w << 4;
             if (pass_bits == 0 && pw >= shift && pw + 16u <= p_end) {
 #pragma unroll
                 for (u32 j = 0; j < 16; ++j) {
                     const u32 x = __funnelshift_l(w1, w0, 2 * j);
-                    table[(x >> sh) & (KMER16_SLOTS - 1u)] = (uint16_t)(pw + j);
+                    table8[x >> slot_sh] = (uint8_t)((x >> sh) | 0x80u);
                 }
             } else {
                 u32 m = 0xFFFFu;
@@ -136,14 +176,14 @@ static __device__ bool k16_count(const u32 *tile, uint16_t *table, uint16_t *lis
 #pragma unroll 4
                 for (u32 j = 0; j < 16; ++j) {
                     const u32 x = __funnelshift_l(w1, w0, 2 * j);
-                    if (((m >> j) & 1u) && (pass_bits == 0 || (x >> cls_sh) == pass))
-                        table[(x >> sh) & (KMER16_SLOTS - 1u)] = (uint16_t)(pw + j);
+                    if (((m >> j) & 1u) && (pass_bits == 0 || ((x >> cls_sh) & (n_pass - 1u)) == pass))
+                        table8[x >> slot_sh] = (uint8_t)((x >> sh) | 0x80u);
                 }
             }
         }
-        __syncthreads();
-        // ---- dense round, read back; losers are appended to list_a ----
-        for (u32 w_base = threadIdx.x & ~31u; w_base < n_scan; w_base += KMER16_THREADS) { // warp-uniform trip count
+        k16_sync_consumers();
+        // ---- dense round, read back; k-mers whose key does not own its slot go to list_a ----
+        for (u32 w_base = threadIdx.x & ~31u; w_base < n_scan; w_base += KMER16_CONSUMERS) { // warp-uniform trip count
             const u32 w = w_base + lane;
             u32 pend = 0, pw = w << 4;
             if (w < n_scan) {
@@ -152,9 +192,8 @@ static __device__ bool k16_count(const u32 *tile, uint16_t *table, uint16_t *lis
 #pragma unroll
                     for (u32 j = 0; j < 16; ++j) {
                         const u32 x = __funnelshift_l(w1, w0, 2 * j);
-                        const u32 v = table[(x >> sh) & (KMER16_SLOTS - 1u)];
-                        if (v == pw + j) ++mine;
-                        else if ((x ^ k16_kmer_at(tile, v)) >> sh) pend |= 1u << j;
+                        const u32 v = table8[x >> slot_sh];
+                        pend |= (v != (((x >> sh) | 0x80u) & 0xFFu)) ? (1u << j) : 0u;
                     }
                 } else {
                     u32 m = 0xFFFFu;
@@ -163,32 +202,36 @@ static __device__ bool k16_count(const u32 *tile, uint16_t *table, uint16_t *lis
 #pragma unroll 4
                     for (u32 j = 0; j < 16; ++j) {
                         const u32 x = __funnelshift_l(w1, w0, 2 * j);
-                        if (((m >> j) & 1u) && (pass_bits == 0 || (x >> cls_sh) == pass)) {
-                            const u32 v = table[(x >> sh) & (KMER16_SLOTS - 1u)];
-                            if (v == pw + j) ++mine;
-                            else if ((x ^ k16_kmer_at(tile, v)) >> sh) pend |= 1u << j;
+                        if (((m >> j) & 1u) && (pass_bits == 0 || ((x >> cls_sh) & (n_pass - 1u)) == pass)) {
+                            const u32 v = table8[x >> slot_sh];
+                            pend |= (v != (((x >> sh) | 0x80u) & 0xFFu)) ? (1u << j) : 0u;
                         }
                     }
                 }
             }
             k16_append(pend, pw, list_a, &s_cnt[0], lane, list_cap);
         }
-        __syncthreads();
+        // ---- the keys resolved by this round = the non-empty byte slots (every stored byte has bit 7 set) ----
+        for (u32 i = threadIdx.x; i < KMER16_TABLE_BYTES / 16u; i += KMER16_CONSUMERS) {
+            const uint4 q = ((const uint4 *)table8)[i];
+            mine += __popc(((q.x & 0x80808080u) >> 3) | ((q.y & 0x80808080u) >> 2) | ((q.z & 0x80808080u) >> 1) | (q.w & 0x80808080u));
+        }
+        k16_sync_consumers();
         u32 n_list = s_cnt[0];
         if (n_list > list_cap) return false;
-        // ---- list rounds ----
+        // ---- list rounds: u16 position tags, winner's key checked against the staged stream ----
         uint16_t *cur = list_a, *nxt = list_b;
         u32 ci = 1, round = 0;
         while (n_list > 32u) {
             ++round;
             const u32 mult = 0x9E3779B1u + 0x3C6EF372u * round; // odd
-            for (u32 i = threadIdx.x; i < n_list; i += KMER16_THREADS) {
+            for (u32 i = threadIdx.x; i < n_list; i += KMER16_CONSUMERS) {
                 const u32 pos = cur[i];
                 const u32 key = k16_kmer_at(tile, pos) >> sh;
                 table[(key * mult) >> 17] = (uint16_t)pos;
             }
-            __syncthreads();
-            for (u32 i0 = threadIdx.x & ~31u; i0 < n_list; i0 += KMER16_THREADS) { // warp-uniform trip count
+            k16_sync_consumers();
+            for (u32 i0 = threadIdx.x & ~31u; i0 < n_list; i0 += KMER16_CONSUMERS) { // warp-uniform trip count
                 const u32 i = i0 + lane;
                 bool lost = false;
                 u32 pos = 0;
@@ -207,7 +250,7 @@ static __device__ bool k16_count(const u32 *tile, uint16_t *table, uint16_t *lis
                     if (lost) nxt[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)pos; // <= n_list entries: fits
                 }
             }
-            __syncthreads();
+            k16_sync_consumers();
             n_list = s_cnt[ci];
             ci ^= 1u;
             if (threadIdx.x == 0) s_cnt[ci] = 0; // next round's counter; nobody reads it before the next barrier
@@ -223,58 +266,107 @@ static __device__ bool k16_count(const u32 *tile, uint16_t *table, uint16_t *lis
     return true;
 }
 
+static __device__ __forceinline__ void k16_finish_piece(tgsf_piece *pieces, u32 pi, int len, int repeat, const DevParams &P,
+                                                        u64 *counters) {
+    pieces[pi].repeat_len = repeat;
+    if (repeat < P.min_repeat) { // T.cpp:1984-1988
+        pieces[pi].status = TGSF_PIECE_SHORT_REPEAT;
+        atomic_add_u64(counters + P.L.drop_info + 15, 1ull);
+        atomic_add_u64(counters + P.L.drop_info + 16, (u64)len);
+    }
+}
+
 __global__ void __launch_bounds__(KMER16_THREADS, 2)
 k_kmer_tag16(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pieces_ptr,
              u64 *__restrict__ counters, const u32 *__restrict__ dev_status, u32 *__restrict__ work_ctr,
              u32 *__restrict__ long_list, u32 *__restrict__ n_long, u32 list_cap) { // list_cap <= KMER16_LIST_CAP (smaller: tests)
     if (*dev_status != DEV_STATUS_OK) return;
     extern __shared__ __align__(16) uint8_t k16mem[];
-    uint16_t *table = (uint16_t *)k16mem;
-    u32 *tile = (u32 *)(k16mem + KMER16_SLOTS * 2u);
-    uint16_t *list_a = (uint16_t *)(tile + KMER16_TILE_WORDS + 2u);
+    uint8_t *table = k16mem;
+    u32 *tiles = (u32 *)(k16mem + KMER16_TABLE_BYTES);
+    uint16_t *list_a = (uint16_t *)(k16mem + KMER16_TABLE_BYTES + 2u * KMER16_TILE_BYTES);
     uint16_t *list_b = list_a + KMER16_LIST_CAP;
     __shared__ u32 s_cnt[2];
-    __shared__ u32 s_distinct, s_pi;
+    __shared__ u32 s_distinct;
+    __shared__ K16Meta s_meta[2];
     const int k = P.kmer;
     const u32 n_pieces = *n_pieces_ptr;
-    const u64 n_total = B.offsets[B.n_reads];
+    // barriers: 1 = consumers; 2 + b = tile b full (its producer arrives, consumers wait); 4 + b = tile b empty
 
-    for (;;) {
-        __syncthreads(); // everyone is done with s_pi / s_distinct / the tile of the previous piece
-        if (threadIdx.x == 0) { s_pi = atomicAdd(work_ctr, 1u); s_distinct = 0; }
-        __syncthreads();
-        const u32 pi = s_pi;
-        if (pi >= n_pieces) return;
-        tgsf_piece pc = pieces[pi];
-        if (pc.status != TGSF_PIECE_EMIT) continue;
-        const int total = pc.len - k + 1;
-        if (total > (int)KMER16_MAX_KMERS) { // too long for 16-bit positions: k_kmer_smem takes it
-            if (threadIdx.x == 0) long_list[atomicAdd(n_long, 1u)] = pi;
-            continue;
-        }
-        if (total > 0) {
+    if (threadIdx.x >= KMER16_CONSUMERS) { // ---------------- producer warps: warp p fills tile p ----------------
+        const u32 lane = threadIdx.x & 31u;
+        const u32 b = (threadIdx.x - KMER16_CONSUMERS) >> 5;
+        const u64 n_total = B.offsets[B.n_reads];
+        for (u32 n = 0;; ++n) {
+            u32 pi;
+            tgsf_piece pc;
+            int total = 0;
+            for (;;) { // next piece this kernel counts
+                pi = 0;
+                if (lane == 0) pi = atomicAdd(work_ctr, 1u);
+                pi = __shfl_sync(0xffffffffu, pi, 0);
+                if (pi >= n_pieces) break;
+                pc = pieces[pi];
+                if (pc.status != TGSF_PIECE_EMIT) continue;
+                total = pc.len - k + 1;
+                if (total > (int)KMER16_MAX_KMERS) { // too long for 16-bit positions: k_kmer_smem takes it
+                    if (lane == 0) long_list[atomicAdd(n_long, 1u)] = pi;
+                    continue;
+                }
+                if (total <= 0) { // no k-mer at all: see oracle/tgsf_oracle.c kmer_repeat_len
+                    if (lane == 0) k16_finish_piece(pieces, pi, pc.len, total - 1, P, counters);
+                    continue;
+                }
+                break;
+            }
+            // (the metadata chain above ran while the consumers were still counting this tile's previous piece)
+            if (n >= 1u) k16_bar_sync(4u + b, KMER16_CONSUMERS + 32u); // the consumers are done with tile b
+            if (pi >= n_pieces) {
+                if (lane == 0) s_meta[b].pi = KMER16_END;
+                __threadfence_block();
+                __syncwarp();
+                k16_bar_arrive(2u + b, KMER16_CONSUMERS + 32u);
+                return;
+            }
             const u64 seq0 = B.offsets[pc.read] + (u64)pc.start; // absolute offset of the piece
             const u64 abase = seq0 & ~15ull;
             const u32 shift = (u32)(seq0 - abase);
-            k16_stage(B, n_total, abase, (shift + (u32)total + (u32)k - 1u + 15u) / 16u, tile);
-            u32 pass_bits = 0;
-            while (((u32)total >> pass_bits) > KMER16_ONE_PASS) ++pass_bits;
-            u32 mine = 0;
-            // (the barrier at the top of k16_count orders the staging before the first table round)
-            while (!k16_count(tile, table, list_a, list_b, s_cnt, shift, shift + (u32)total, k, pass_bits, list_cap, mine)) ++pass_bits;
-            mine = warp_sum_u32(mine);
-            if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(&s_distinct, mine);
-            __syncthreads();
+            k16_stage(B, n_total, abase, (shift + (u32)total + (u32)k - 1u + 15u) / 16u, tiles + b * (KMER16_TILE_WORDS + 2u), lane);
+            if (lane == 0) { s_meta[b].pi = pi; s_meta[b].shift = shift; s_meta[b].total = total; s_meta[b].len = pc.len; }
+            __threadfence_block();
+            __syncwarp();
+            k16_bar_arrive(2u + b, KMER16_CONSUMERS + 32u);
         }
-        if (threadIdx.x == 0) {
-            const int repeat = total > 0 ? total - (int)s_distinct : total - 1; // see oracle/tgsf_oracle.c kmer_repeat_len
-            pc.repeat_len = repeat;
-            if (repeat < P.min_repeat) { // T.cpp:1984-1988
-                pc.status = TGSF_PIECE_SHORT_REPEAT;
-                atomic_add_u64(counters + P.L.drop_info + 15, 1ull);
-                atomic_add_u64(counters + P.L.drop_info + 16, (u64)pc.len);
-            }
-            pieces[pi] = pc;
+    }
+
+    // ---------------- consumer warps: tiles in turn until both producers have signalled the end ----------------
+    u32 ended = 0;
+    for (u32 n = 0;; ++n) {
+        const u32 b = n & 1u;
+        if (ended & (1u << b)) continue; // (the other tile is still live, or the loop would have returned)
+        k16_bar_sync(2u + b, KMER16_CONSUMERS + 32u); // tile b and its meta are ready
+        const K16Meta M = s_meta[b];
+        if (M.pi == KMER16_END) {
+            ended |= 1u << b;
+            if (ended == 3u) return;
+            continue;
         }
+        const u32 *tile = tiles + b * (KMER16_TILE_WORDS + 2u);
+        if (threadIdx.x == 0) s_distinct = 0; // ordered before its use by the barriers inside k16_count
+        // classes split the key REMAINDER (2k - 16 bits; none for k <= 8, where slot = key and nothing can collide)
+        const u32 rem_bits = 2 * k > 16 ? (u32)(2 * k - 16) : 0u;
+        u32 pass_bits = rem_bits > 7u ? rem_bits - 7u : 0u; // an owner byte holds 7 remainder bits: k = 12 needs two classes
+        while (pass_bits < rem_bits && ((u32)M.total >> pass_bits) > KMER16_ONE_PASS) ++pass_bits;
+        u32 mine = 0;
+        if (k == 11) {
+            while (!k16_count<11>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
+        } else {
+            while (!k16_count<0>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
+        }
+        mine = warp_sum_u32(mine);
+        if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(&s_distinct, mine);
+        k16_sync_consumers();
+        if (threadIdx.x == 0) k16_finish_piece(pieces, M.pi, M.len, M.total - (int)s_distinct, P, counters);
+        k16_bar_arrive(4u + b, KMER16_CONSUMERS + 32u); // tile b may be refilled
     }
 }
