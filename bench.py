@@ -1,29 +1,37 @@
 #!/usr/bin/env python
 """bench.py — filtered Gbases/s of the per-read filter/trim hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--reads R]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--config C] [--strong] [--reads R]
 
 One "step" = one pass of the whole hot path (K1 raw scan -> K3 adapter search -> K5 regions ->
-[K4] -> K1 clean scan) over one batch of synthetic reads.  Workload at N=1: BASELINE config[1]
-(synthetic ONT, 200 000 reads, N50 ~30 kb, planted 5' adapter, `-x ont` with adapter
-auto-identify + end trim); every rank of a multi-GPU run processes its own shard of that size
-(weak scaling, no data-path collective; the QC counters are combined with one NCCL allreduce
-after the timed region).
+[K4] -> K1 clean scan) over the workload's batches.  Workload (`--config`, or TGSF_BENCH_CONFIG;
+BASELINE config index + 1): default 2 = configs[1], 200 000 synthetic ONT reads, N50 ~30 kb, planted
+5' adapter, `-x ont` with adapter auto-identify + end trim.
+  weak scaling (default): every rank processes its own dataset of the config's full size; no data-path
+      collective, the QC counters are combined with one NCCL allreduce after the timed region.
+  strong scaling (`--strong`, or TGSF_BENCH_STRONG=1): ONE dataset of the config's full size, cut into
+      16 batches that are dealt round-robin to the ranks (tgsfilter_b200.shard); the counter allreduce is
+      INSIDE the reported time of every step.
+Datasets of more than 400 000 reads are fed as several batches through the context's two slots.
 
-`value`  : input bases / device time, inputs resident in HBM (CUDA events on the library's stream)
-`e2e`    : same metric through the C-ABI with pinned HOST buffers, H2D + kernels + D2H of the results
-           inside the timed region, in the input format the C++ host (src/TGSFilter.cpp) feeds:
-           2-bit packed bases + Phred bytes (tgsf_submit_packed); `e2e_bytes` is the same through
-           tgsf_submit with one byte per base.  Both are PCIe-bound.
-`roofline`: dominant kernel (K3 k_mid_scan, INT-ALU bound per SURVEY.md §8(d)); the HBM-bound K1
-           scan is reported next to it under `roofline_kernels`
-`cpu_baseline`: the UNMODIFIED reference CLI (oracle/_ref/tgsfilter) on a bounded sample of the
-           same workload on this box's host cores.
+`value`  : input bases / device time, inputs resident in HBM.  Device time of a step = last kernel end
+           - first kernel start of its batches on the device clock (tgsf_last_span; batches in the two
+           slots run on two streams and overlap) [+ the allreduce in strong mode], max over ranks.
+`e2e`    : same metric through the C-ABI with pinned HOST buffers: H2D + unpack + kernels + D2H of the
+           results inside the timed region (wall clock between barriers, max over ranks).
+`roofline`: dominant kernel; the others under `roofline_kernels`.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference CLI (oracle/_ref/tgsfilter) on this box's
+           host cores over the SAME workload (rank 0's dataset, written as FASTQ to tmpfs).  The
+           reference arm runs the full dataset every step unless that would exceed its time budget
+           (TGSF_REF_BUDGET_S, default 600 s for all warm-up + timed steps); then every step is the
+           largest prefix of the dataset that fits, and `cpu_baseline.sample` says so.
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import shutil
 import subprocess
@@ -44,6 +52,41 @@ CONFIG_CLI = {1: ["-x", "hifi"], 2: ["-x", "ont"], 3: ["-x", "ont", "-M", "35", 
               5: ["-x", "hifi", "-k", "11", "-p", "5000"]}
 CONFIG_TYPE = {1: "hifi", 2: "ont", 3: "ont", 4: "clr", 5: "hifi"}
 REF_CLI = os.path.join(ROOT, "oracle", "_ref", "tgsfilter")
+SUB_READS = 400_000      # weak mode: datasets above this many reads are fed as several batches
+STRONG_BATCHES = 16      # strong mode: the dataset is always dealt as this many batches
+SEED0 = 20261017
+
+
+def batch_seed(cfg: int, rank: int, j: int) -> int:
+    return SEED0 + cfg + 1000 * rank + 100000 * j
+
+
+def plan_batches(cfg: int, n_total: int, world: int, rank: int, strong: bool):
+    """[(global batch index, reads, seed)] this rank generates and processes."""
+    if strong:
+        nb = min(STRONG_BATCHES, n_total)
+        sizes = [n_total // nb + (1 if j < n_total % nb else 0) for j in range(nb)]
+        return [(j, sizes[j], batch_seed(cfg, 0, j)) for j in range(nb) if j % world == rank]
+    nb = max(1, math.ceil(n_total / SUB_READS))
+    sizes = [n_total // nb + (1 if j < n_total % nb else 0) for j in range(nb)]
+    return [(j, sizes[j], batch_seed(cfg, rank, j)) for j in range(nb)]
+
+
+def workload_name(cfg: int, n_reads: int, strong: bool) -> str:
+    names = {1: "config[0] synthetic HiFi FASTQ ~15 kb, -x hifi",
+             2: "config[1] synthetic ONT FASTQ N50 ~30 kb, planted 5' adapter, -x ont (auto-identify + end trim)",
+             3: "config[2] synthetic ONT ultra-long N50 ~100 kb, planted middle adapters, -M 35 -T 50",
+             4: "config[3] synthetic PacBio CLR, -q 7 -Q 15 -e 150 -b 1",
+             5: "config[4] synthetic HiFi, -k 11 -p 5000"}
+    return f"{names[cfg]}; {n_reads} reads " + ("in total, dealt to the GPUs" if strong else "per GPU")
+
+
+def static_config(cfg: int, n_reads: int, strong: bool) -> dict:
+    """The `config` object: a pure function of the command line, identical in both arms."""
+    return {"workload": workload_name(cfg, n_reads, strong), "cli": " ".join(CONFIG_CLI[cfg]),
+            "reads": n_reads, "reads_are": "total over all GPUs" if strong else "per GPU",
+            "seed": SEED0 + cfg,
+            "l2": "inputs (2 B/base, >= 0.5 GB per launch) are larger than the 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -224,82 +267,169 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def __enter__(self):
+        if shutil.which("nvidia-smi") is None:
+            return self
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+        time.sleep(0.3)
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                continue
+        busy = sorted(sm)[len(sm) // 2:] if sm else []  # upper half ~ samples under load
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
 # ------------------------------------------------------------------------------------------------
-# reference on the host CPU (bounded sample)
+# reference on the host CPU
 # ------------------------------------------------------------------------------------------------
-def reference_sample_fastq(config: int, sample_reads: int) -> bytes:
-    from tgsfilter_b200 import synth
-    batch = synth.make_config(config, sample_reads, with_names=False)
-    return batch.to_fastq(), batch.n_bases
-
-
-def time_reference(config: int, fq_path: str, n_bases: int, threads: int, repeats: int = 1):
-    out = os.path.join(os.path.dirname(fq_path), "ref_out.fq")
-    best = None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        pr = subprocess.run([REF_CLI, "-i", fq_path, "-o", out, "-t", str(threads)] + CONFIG_CLI[config],
-                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=os.path.dirname(fq_path))
-        dt = time.perf_counter() - t0
-        if pr.returncode != 0:
-            raise RuntimeError("reference CLI failed: " + pr.stderr.decode()[-400:])
-        best = dt if best is None else min(best, dt)
-    return n_bases / best / 1e9, best
-
-
 def ref_threads() -> int:
     n = os.cpu_count() or 2
     return max(1, min(32, n - 1))  # the reference's own clamp, T.cpp:488-499
+
+
+def write_reference_fastq(cfg: int, plan, path: str, max_reads: int = 0):
+    """The reads of `plan` (rank 0's batches) as one FASTQ file; same generator and seeds as the GPU arm when a
+    CUDA device is there (it is on the bench box), the numpy generator of tgsfilter_b200.synth otherwise.
+    Returns (reads, bases, generator name)."""
+    from tgsfilter_b200 import synth
+    use_gpu = False
+    try:
+        import torch
+        use_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    reads = bases = 0
+    with open(path, "wb", buffering=1 << 24) as f:
+        for j, n, seed in plan:
+            if max_reads and reads >= max_reads:
+                break
+            take = n if not max_reads else min(n, max_reads - reads)
+            if use_gpu:
+                import torch
+                dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+                d_b, d_q, _, offsets, total = gen_workload_gpu(cfg, n, seed, dev)
+                hb, hq = d_b[:total].cpu().numpy(), d_q[:total].cpu().numpy()
+                del d_b, d_q
+                torch.cuda.empty_cache()
+            else:
+                b = synth.make_config(cfg, n, with_names=False)
+                hb, hq, offsets = b.bases, b.quals, b.offsets.astype(np.int64)
+            synth.write_fastq_to(f, hb, hq, offsets[:take + 1], b"b%d_" % j)
+            reads += take
+            bases += int(offsets[take])
+            del hb, hq
+    return reads, bases, "bench.gen_workload_gpu" if use_gpu else "tgsfilter_b200.synth (numpy; no CUDA device here)"
+
+
+def run_reference_once(cfg: int, fq_path: str, threads: int) -> float:
+    out = os.path.join(os.path.dirname(fq_path), "ref_out.fq")
+    t0 = time.perf_counter()
+    pr = subprocess.run([REF_CLI, "-i", fq_path, "-o", out, "-t", str(threads)] + CONFIG_CLI[cfg],
+                        stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, cwd=os.path.dirname(fq_path))
+    dt = time.perf_counter() - t0
+    if pr.returncode != 0:
+        raise RuntimeError("reference CLI failed: " + pr.stderr.decode()[-400:])
+    try:
+        os.unlink(out)
+    except OSError:
+        pass
+    return dt
+
+
+def shm_dir():
+    return "/dev/shm" if os.path.isdir("/dev/shm") else None
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cfg = args.config
+    cfg, strong = args.config, args.strong
+    n_total = args.reads or CONFIG_READS[cfg]
     if not os.path.exists(REF_CLI):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/tgsfilter not built"}))
         return 0
     threads = ref_threads()
-    sample_reads = args.sample_reads
-    tmpdir = tempfile.mkdtemp(prefix="tgsf_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    budget = float(os.environ.get("TGSF_REF_BUDGET_S", "600"))
+    plan = plan_batches(cfg, n_total, 1, 0, strong)
+    tmpdir = tempfile.mkdtemp(prefix="tgsf_ref_", dir=shm_dir())
+    t_begin = time.perf_counter()
     try:
-        fq, n_bases = reference_sample_fastq(cfg, sample_reads)
         fq_path = os.path.join(tmpdir, "sample.fq")
-        with open(fq_path, "wb") as f:
-            f.write(fq)
-        for _ in range(args.warmup):
-            time_reference(cfg, fq_path, n_bases, threads)
+        reads, bases, gen = write_reference_fastq(cfg, plan, fq_path, args.sample_reads)
+        # one calibration run (it is also the first warm-up step): does (warmup + steps) x full fit the budget?
+        t_full = run_reference_once(cfg, fq_path, threads)
+        runs_left = max(args.warmup - 1, 0) + args.steps
+        left = budget - (time.perf_counter() - t_begin)
+        if runs_left * t_full > left and reads > 6000:
+            frac = max(left / (runs_left * t_full), 0.02)
+            reads_s = max(6000, int(reads * frac) // 1000 * 1000)
+            reads, bases, gen = write_reference_fastq(cfg, plan, fq_path, reads_s)
+            run_reference_once(cfg, fq_path, threads)
+        for _ in range(max(args.warmup - 1, 0)):
+            run_reference_once(cfg, fq_path, threads)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            time_reference(cfg, fq_path, n_bases, threads)
+            run_reference_once(cfg, fq_path, threads)
         dt = time.perf_counter() - t0
     finally:
         shutil.rmtree(tmpdir, ignore_errors=True)
-    value = n_bases * args.steps / dt / 1e9
-    sample = f"first {sample_reads} reads of the config-{cfg} generator ({n_bases} bases), FASTQ on tmpfs -> FASTQ on tmpfs"
+    value = bases * args.steps / dt / 1e9
+    whole = reads == sum(n for _, n, _ in plan)
+    sample = (f"{'the whole dataset' if whole else 'the first ' + str(reads) + ' reads of the dataset'} of rank 0 "
+              f"({reads} reads, {bases} bases, generator {gen}), FASTQ on tmpfs -> FASTQ on tmpfs, unmodified "
+              f"reference CLI -t {threads}, {dt / args.steps:.1f} s per step")
     line = {
         "impl": "reference", "metric": "filtered Gbases/s", "value": value, "unit": "Gbases/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "u8/u64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, CONFIG_READS[cfg]), "cli": " ".join(CONFIG_CLI[cfg]),
-                   "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": threads, "kind": "reference",
-                         "sample": sample},
+        "config": static_config(cfg, n_total, strong),
+        "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
     return 0
-
-
-def workload_name(cfg: int, n_reads: int) -> str:
-    names = {1: "config[0] synthetic HiFi FASTQ ~15 kb, -x hifi",
-             2: "config[1] synthetic ONT FASTQ N50 ~30 kb, planted 5' adapter, -x ont (auto-identify + end trim)",
-             3: "config[2] synthetic ONT ultra-long N50 ~100 kb, planted middle adapters, -M 35 -T 50",
-             4: "config[3] synthetic PacBio CLR, -q 7 -Q 15 -e 150 -b 1",
-             5: "config[4] synthetic HiFi, -k 11 -p 5000"}
-    return f"{names[cfg]}; {n_reads} reads per GPU"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -311,13 +441,19 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", type=int, default=2, help="BASELINE config index + 1 (2 = configs[1])")
-    ap.add_argument("--reads", type=int, default=0, help="reads per GPU (0 = the config's full size)")
-    ap.add_argument("--sample-reads", type=int, default=6000, help="reads in the CPU reference sample")
+    ap.add_argument("--config", type=int, default=int(os.environ.get("TGSF_BENCH_CONFIG", "2")),
+                    help="BASELINE config index + 1 (2 = configs[1]); env TGSF_BENCH_CONFIG")
+    ap.add_argument("--strong", action="store_true", default=os.environ.get("TGSF_BENCH_STRONG", "") not in ("", "0"),
+                    help="strong scaling: one dataset dealt to the ranks, counter allreduce inside the step; env TGSF_BENCH_STRONG=1")
+    ap.add_argument("--reads", type=int, default=0, help="reads in the dataset (0 = the config's full size)")
+    ap.add_argument("--sample-reads", type=int, default=0, help="CPU reference: cap the reads per step (0 = whole dataset / time budget)")
     ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-fed measurement (profiling runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.config not in CONFIG_READS:
+        raise SystemExit(f"--config must be one of {sorted(CONFIG_READS)}")
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -340,20 +476,33 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    cfg = args.config
-    n_reads = args.reads or CONFIG_READS[cfg]
+    cfg, strong = args.config, args.strong
+    n_total = args.reads or CONFIG_READS[cfg]
     read_type = CONFIG_TYPE[cfg]
-    d_bases, d_quals, d_off, offsets, n_bases = gen_workload_gpu(cfg, n_reads, 20261017 + cfg + 1000 * rank, device)
+    plan = plan_batches(cfg, n_total, world, rank, strong)
 
-    # host copies (pinned) for the end-to-end path and the pre-pass sampling
-    h_bases = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
-    h_quals = torch.empty(n_bases, dtype=torch.uint8, pin_memory=True)
-    h_bases.copy_(d_bases[:n_bases])
-    h_quals.copy_(d_quals[:n_bases])
+    # ---- resident batches + pinned host copies
+    class B:
+        pass
+    batches = []
+    for j, n, seed in plan:
+        b = B()
+        b.j, b.n_reads = j, n
+        b.d_bases, b.d_quals, b.d_off, b.offsets, b.n_bases = gen_workload_gpu(cfg, n, seed, device)
+        batches.append(b)
+    local_bases = sum(b.n_bases for b in batches)
+    local_reads = sum(b.n_reads for b in batches)
+    want_e2e = not args.no_e2e
+    for b in batches:
+        if want_e2e or b is batches[0]:
+            b.h_bases = torch.empty(b.n_bases, dtype=torch.uint8, pin_memory=True)
+            b.h_quals = torch.empty(b.n_bases, dtype=torch.uint8, pin_memory=True)
+            b.h_bases.copy_(b.d_bases[:b.n_bases])
+            b.h_quals.copy_(b.d_quals[:b.n_bases])
     torch.cuda.synchronize()
-    host_batch = ReadBatch(h_bases.numpy(), h_quals.numpy(), offsets.astype(np.uint64))
 
-    # parameters exactly as the CLI would resolve them for this config
+    # ---- parameters exactly as the CLI would resolve them for this config (pre-pass on the first batch of the
+    # dataset; in strong mode rank 0 owns that batch and broadcasts the decision)
     cli = CONFIG_CLI[cfg]
     p = FilterParams().apply_read_type(read_type)
     if "-q" in cli:
@@ -363,12 +512,48 @@ def main():
     if "-p" in cli:
         p.min_repeat = int(cli[cli.index("-p") + 1])
     t0 = time.perf_counter()
-    params, pre = prepass.run_prepass(host_batch, p, read_type, device=local_rank)
+    params = None
+    if not strong or rank == 0:
+        # the CLI samples the first 100 000 usable reads of the FILE: take the leading batches of the dataset
+        # until they hold that many reads (batches that live on other ranks are regenerated here just for this)
+        lead, have = [], 0
+        full_plan = plan_batches(cfg, n_total, 1, 0, strong) if strong else plan
+        by_j = {b.j: b for b in batches}
+        for j, n, seed in full_plan:
+            if have >= 100_000:
+                break
+            if j in by_j and hasattr(by_j[j], "h_bases"):
+                b = by_j[j]
+                lead.append((b.h_bases.numpy(), b.h_quals.numpy(), b.offsets))
+            else:
+                d_b, d_q, _, offs, tot = gen_workload_gpu(cfg, n, seed, device)
+                lead.append((d_b[:tot].cpu().numpy(), d_q[:tot].cpu().numpy(), offs))
+                del d_b, d_q
+            have += n
+        if len(lead) == 1:
+            hb, hq, ho = lead[0]
+        else:
+            hb = np.concatenate([x[0] for x in lead])
+            hq = np.concatenate([x[1] for x in lead])
+            parts, base = [np.zeros(1, np.int64)], 0
+            for x in lead:
+                parts.append(x[2][1:] + base)
+                base += int(x[2][-1])
+            ho = np.concatenate(parts)
+        host_batch = ReadBatch(hb, hq, ho.astype(np.uint64))
+        params, _pre = prepass.run_prepass(host_batch, p, read_type, device=local_rank)
+        del lead, hb, hq, host_batch
+        torch.cuda.empty_cache()
+    if strong and world > 1:
+        box = [params]
+        dist.broadcast_object_list(box, src=0)
+        params = box[0]
     prepass_ms = (time.perf_counter() - t0) * 1e3
     params.n_slots = 2
-
+    max_len = max(int(np.diff(b.offsets).max()) for b in batches)
+    if max_len > 4_000_000:
+        params.max_read_len = max_len
     eng = FilterEngine(params, device=local_rank)
-    off_u64 = d_off  # int64 with the same bit pattern as uint64
 
     def barrier():
         torch.cuda.synchronize()
@@ -376,60 +561,88 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        eng.submit_device(d_bases.data_ptr(), d_quals.data_ptr(), off_u64.data_ptr(), n_reads, n_bases)
-        eng.collect(want_results=False)
-        return eng.last_timing()[0], eng.last_stage_ms()
+    # zero-copy view of the device counter block (allreduce operand)
+    blk = scratch = None
+    if world > 1:
+        ptr, nwords = eng.counters_device_ptr()
 
-    # sub-batches of the end-to-end path (host buffers; two slots -> copy / compute overlap)
-    bounds = np.linspace(0, n_reads, args.e2e_chunks + 1).astype(np.int64)
-    sub = []
-    for a, b in zip(bounds[:-1], bounds[1:]):
-        if b > a:
-            o = (offsets[a:b + 1] - offsets[a]).astype(np.uint64)
-            o_t = torch.from_numpy(o.view(np.int64)).pin_memory()
-            sub.append((int(offsets[a]), int(b - a), o_t, int(offsets[b] - offsets[a])))
-    d2h_bytes = 0
+        class _Blk:
+            __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        blk = torch.as_tensor(_Blk(), device=device)
+        scratch = torch.zeros(nwords, dtype=torch.int64, device=device)
+        dist.all_reduce(scratch, op=dist.ReduceOp.SUM)  # NCCL sets its channels up lazily
+        torch.cuda.synchronize()
+    ar_ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
 
-    # 2-bit packed copy of every sub-batch (what the C++ host's parser produces with tgsf_pack_bases;
-    # the synthetic bases are pure upper-case ACGT, so the exception list is empty)
-    pk_off = [0]
-    for _, _, _, nb in sub:
-        pk_off.append(pk_off[-1] + ((nb + 3) // 4 + 63) // 64 * 64)
-    h_packed = torch.empty(pk_off[-1] + 64, dtype=torch.uint8, pin_memory=True)
-    for (s0, nr, o_t, nb), po in zip(sub, pk_off[:-1]):
-        b = d_bases[s0:s0 + nb]
-        if nb % 4:
-            b = torch.cat([b, torch.full((4 - nb % 4,), 65, dtype=torch.uint8, device=device)])
-        code = (b >> 1) & 3
-        code = (code ^ (code >> 1)).view(-1, 4)          # A0 C1 G2 T3
-        pk = code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)
-        h_packed[po:po + pk.numel()].copy_(pk)
-        del b, code, pk
-    torch.cuda.synchronize()
-
-    def step_e2e_packed():
+    def step_resident(stage_acc):
+        """All local batches through the two slots; returns the step's device time in ms."""
+        spans = []
         inflight = 0
-        for (s0, nr, o_t, nb), po in zip(sub, pk_off[:-1]):
+
+        def retire():
+            eng.collect(want_results=False)
+            spans.append(eng.last_span())
+            st = eng.last_stage_ms()
+            for k in stage_acc:
+                stage_acc[k] += st[k]
+        for b in batches:
             if inflight == 2:
-                eng.collect()
+                retire()
                 inflight -= 1
-            eng.submit_packed_raw(h_packed.data_ptr() + po, h_quals.data_ptr() + s0, o_t.data_ptr(), nr)
+            eng.submit_device(b.d_bases.data_ptr(), b.d_quals.data_ptr(), b.d_off.data_ptr(), b.n_reads, b.n_bases)
             inflight += 1
         while inflight:
-            eng.collect()
+            retire()
             inflight -= 1
+        ms = max(e for _, e in spans) - min(s for s, _ in spans) if spans else 0.0
+        if strong and world > 1:  # the QC counters of the dataset: one allreduce, inside the step
+            ar_ev[0].record()
+            scratch.copy_(blk)
+            dist.all_reduce(scratch, op=dist.ReduceOp.SUM)
+            ar_ev[1].record()
+            ar_ev[1].synchronize()
+            ms += ar_ev[0].elapsed_time(ar_ev[1])
+        return ms
 
-    def step_e2e():
+    # ---- sub-batches of the end-to-end path (host buffers; two slots -> copy / compute overlap)
+    sub = []          # (batch, first base, reads, pinned offsets, bases, packed offset)
+    pk_total = 0
+    if want_e2e:
+        per = max(1, args.e2e_chunks // len(batches))
+        for b in batches:
+            bounds = np.linspace(0, b.n_reads, per + 1).astype(np.int64)
+            for a, c in zip(bounds[:-1], bounds[1:]):
+                if c > a:
+                    o = (b.offsets[a:c + 1] - b.offsets[a]).astype(np.uint64)
+                    o_t = torch.from_numpy(o.view(np.int64)).pin_memory()
+                    nb = int(b.offsets[c] - b.offsets[a])
+                    sub.append((b, int(b.offsets[a]), int(c - a), o_t, nb, pk_total))
+                    pk_total += ((nb + 3) // 4 + 63) // 64 * 64
+        # 2-bit packed copy of every sub-batch (what the C++ host's parser produces with tgsf_pack_bases;
+        # the synthetic bases are pure upper-case ACGT, so the exception list is empty)
+        h_packed = torch.empty(pk_total + 64, dtype=torch.uint8, pin_memory=True)
+        for b, s0, nr, o_t, nb, po in sub:
+            x = b.d_bases[s0:s0 + nb]
+            if nb % 4:
+                x = torch.cat([x, torch.full((4 - nb % 4,), 65, dtype=torch.uint8, device=device)])
+            code = (x >> 1) & 3
+            code = (code ^ (code >> 1)).view(-1, 4)          # A0 C1 G2 T3
+            pk = code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)
+            h_packed[po:po + pk.numel()].copy_(pk)
+            del x, code, pk
+        torch.cuda.synchronize()
+    d2h_bytes = 0
+
+    def step_e2e_packed():
         nonlocal d2h_bytes
         d2h = 0
         inflight = 0
-        for s0, nr, o_t, nb in sub:
+        for b, s0, nr, o_t, nb, po in sub:
             if inflight == 2:
                 r, pcs = eng.collect()
                 d2h += r.nbytes + pcs.nbytes
                 inflight -= 1
-            eng.submit_raw(h_bases.data_ptr() + s0, h_quals.data_ptr() + s0, o_t.data_ptr(), nr)
+            eng.submit_packed_raw(h_packed.data_ptr() + po, b.h_quals.data_ptr() + s0, o_t.data_ptr(), nr)
             inflight += 1
         while inflight:
             r, pcs = eng.collect()
@@ -437,11 +650,36 @@ def main():
             inflight -= 1
         d2h_bytes = d2h
 
+    def step_e2e_bytes():
+        inflight = 0
+        for b, s0, nr, o_t, nb, po in sub:
+            if inflight == 2:
+                eng.collect()
+                inflight -= 1
+            eng.submit_raw(b.h_bases.data_ptr() + s0, b.h_quals.data_ptr() + s0, o_t.data_ptr(), nr)
+            inflight += 1
+        while inflight:
+            eng.collect()
+            inflight -= 1
+
+    def timed_wall(fn, steps):
+        barrier()
+        e0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        barrier()
+        t = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     # ---- warm-up
+    dummy = {k: 0.0 for k in _capi.STAGE_NAMES}
     for _ in range(args.warmup):
-        step_resident()
-    step_e2e()
-    step_e2e_packed()
+        step_resident(dummy)
+    if want_e2e:
+        step_e2e_bytes()
+        step_e2e_packed()
     eng.reset_counters()
 
     # ---- timed: resident
@@ -452,72 +690,61 @@ def main():
         wall0 = time.perf_counter()
         dev_ms = 0.0
         for _ in range(args.steps):
-            k_ms, st = step_resident()
-            dev_ms += k_ms
-            for k in stage_sum:
-                stage_sum[k] += st[k]
+            dev_ms += step_resident(stage_sum)
         barrier()
         wall_ms = (time.perf_counter() - wall0) * 1e3
     launches = eng.launch_count() - launches0
     clocks = clk.summary()
     cnt = eng.counters()
+    # per-kernel times for the rooflines: one more pass with ONE batch in flight (stages of batches that overlap in
+    # the two slots stretch each other, so their event times are not kernel times)
+    stage_serial = {k: 0.0 for k in _capi.STAGE_NAMES}
+    serial_ms = 0.0
+    for b in batches:
+        eng.submit_device(b.d_bases.data_ptr(), b.d_quals.data_ptr(), b.d_off.data_ptr(), b.n_reads, b.n_bases)
+        eng.collect(want_results=False)
+        st = eng.last_stage_ms()
+        serial_ms += eng.last_timing()[0]
+        for k in stage_serial:
+            stage_serial[k] += st[k]
     t_dev = torch.tensor([dev_ms], dtype=torch.float64, device=device)
+    t_bases = torch.tensor([float(local_bases)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t_bases, op=dist.ReduceOp.SUM)
     dev_ms_max = float(t_dev.item())
+    total_bases = float(t_bases.item())
 
     # ---- timed: end to end (host buffers)
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
-    barrier()
-    e2e_s = time.perf_counter() - e0
-    t_e2e = torch.tensor([e2e_s], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e2e.item())
+    e2e_value = e2e_packed_value = None
+    pack_gbs = None
+    if want_e2e:
+        e2e_s = timed_wall(step_e2e_bytes, args.steps)
+        e2e_packed_s = timed_wall(step_e2e_packed, args.steps)
+        e2e_value = total_bases * args.steps / e2e_s / 1e9
+        e2e_packed_value = total_bases * args.steps / e2e_packed_s / 1e9
+        # host packer speed (one thread), for context
+        import ctypes
+        b0 = batches[0]
+        nb_probe = min(b0.n_bases, 256 << 20)
+        probe_out = np.empty(nb_probe // 4 + 16, dtype=np.uint8)
+        ne = ctypes.c_uint64(0)
+        tp0 = time.perf_counter()
+        _capi.load().tgsf_pack_bases(b0.h_bases.data_ptr(), nb_probe, probe_out.ctypes.data, None, None, 0, ctypes.byref(ne))
+        pack_gbs = nb_probe / (time.perf_counter() - tp0) / 1e9
 
-    barrier()
-    e0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e_packed()
-    barrier()
-    t_pk = torch.tensor([time.perf_counter() - e0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t_pk, op=dist.ReduceOp.MAX)
-    e2e_packed_s = float(t_pk.item())
-    # host packer speed (one thread), for context
-    nb_probe = min(n_bases, 256 << 20)
-    probe_out = np.empty(nb_probe // 4 + 16, dtype=np.uint8)
-    ne = __import__("ctypes").c_uint64(0)
-    tp0 = time.perf_counter()
-    _capi.load().tgsf_pack_bases(h_bases.data_ptr(), nb_probe, probe_out.ctypes.data, None, None, 0,
-                                 __import__("ctypes").byref(ne))
-    pack_gbs = nb_probe / (time.perf_counter() - tp0) / 1e9
-
-    # ---- final counter allreduce over NVLink (outside the timed region; reported)
+    # ---- final counter allreduce over NVLink (weak mode: outside the timed region; reported)
     allreduce_ms = None
     if world > 1:
-        ptr, nwords = eng.counters_device_ptr()
-
-        class _Blk:  # zero-copy view of the device counter block
-            __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 3}
-        blk = torch.as_tensor(_Blk(), device=device)
-        warm = torch.zeros(nwords, dtype=torch.int64, device=device)  # same size: NCCL sets its channels up lazily
-        dist.all_reduce(warm, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         a0 = time.perf_counter()
         dist.all_reduce(blk, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
         allreduce_ms = (time.perf_counter() - a0) * 1e3
 
-    total_bases = n_bases * world
     value = total_bases * args.steps / (dev_ms_max / 1e3) / 1e9
-    e2e_value = total_bases * args.steps / e2e_s / 1e9
-    e2e_packed_value = total_bases * args.steps / e2e_packed_s / 1e9
 
-    # ---- rooflines
+    # ---- rooflines (this rank's batches)
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -526,10 +753,8 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    lens = np.diff(offsets)
+    lens = np.concatenate([np.diff(b.offsets) for b in batches])
     drop = cnt.drop_info
-    # reads that reach the adapter search = all minus low-quality drops; their middle windows
-    lowq_reads = int(drop[0])
     E = params.end_len
     word_cols_all = 0
     for a in params.adapters:
@@ -537,7 +762,8 @@ def main():
         nw = (q + 63) // 64
         mid = lens - 2 * E
         word_cols_all += nw * int(mid[mid >= q].sum())
-    active_frac = 1.0 - (int(drop[1]) / args.steps) / max(1, n_bases)
+    stage_sum = {k: v * args.steps for k, v in stage_serial.items()}  # (the code below divides by steps)
+    active_frac = 1.0 - (int(drop[1]) / args.steps) / max(1, local_bases)
     word_cols = word_cols_all * active_frac
     mid_ms = stage_sum["mid_scan"] / args.steps
     sm_clock = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
@@ -545,11 +771,13 @@ def main():
     achieved_int = word_cols * 34 / (mid_ms / 1e3) / 1e12 if mid_ms > 0 else 0.0
     raw_ms = stage_sum["raw_scan"] / args.steps
     clean_ms = stage_sum["clean"] / args.steps
-    k1_gbs = 2 * n_bases / (raw_ms / 1e3) / 1e9 if raw_ms > 0 else 0.0
+    k1_gbs = 2 * local_bases / (raw_ms / 1e3) / 1e9 if raw_ms > 0 else 0.0
     step_ms = dev_ms / args.steps if dev_ms else 0.0
-    kept_bases = n_bases - int(drop[1]) // args.steps  # bases entering the clean pass (upper bound)
+    stage_total = sum(stage_sum.values()) / args.steps
+    kept_bases = local_bases - int(drop[1]) // args.steps  # bases entering the clean pass (upper bound)
     clean_gbs = 2 * kept_bases / (clean_ms / 1e3) / 1e9 if clean_ms > 0 else 0.0
     kmer_ms = stage_sum["kmer"] / args.steps
+    share = (lambda ms: ms / stage_total if stage_total else None)
     rl_mid = {"kernel": "k_mid_scan (K3 Myers HW scan, middle windows)", "bound": "int_alu",
               "achieved": achieved_int, "peak": int_peak, "unit": "Tint32op/s",
               "frac": achieved_int / int_peak if int_peak else None, "traffic": None,
@@ -558,34 +786,49 @@ def main():
               "peak_def": f"148 SMs x 128 lanes x {sm_clock:.0f} MHz (median SM clock under load)",
               "note": "ALU-pipe bound (ncu: pipe_alu ~92 % busy); logic ops cannot use the FMA pipe, so "
                       "the 128-lane peak is not reachable: see DESIGN.md §4",
-              "ms": mid_ms, "share_of_step": mid_ms / step_ms if step_ms else None}
+              "ms": mid_ms, "share_of_step": share(mid_ms)}
     rl_raw = {"kernel": "k_scan_tiles_dyn raw pass (K1)", "bound": "hbm", "achieved": k1_gbs, "peak": hbm_peak,
               "unit": "GB/s", "frac": k1_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
-              "work": "2 B per input base", "ms": raw_ms, "share_of_step": raw_ms / step_ms if step_ms else None}
+              "work": "2 B per input base", "ms": raw_ms, "share_of_step": share(raw_ms)}
     rl_clean = {"kernel": "k_scan_tiles_dyn clean pass (K1)", "bound": "hbm", "achieved": clean_gbs,
                 "peak": hbm_peak, "unit": "GB/s", "frac": clean_gbs / hbm_peak, "traffic": None,
                 "peak_source": hbm_src, "work": "2 B per kept base (upper bound: bases of reads passing -q/-Q)",
-                "ms": clean_ms, "share_of_step": clean_ms / step_ms if step_ms else None}
-    rl_kmer = {"kernel": "k_kmer_smem (K4, k <= 12: atomics-free tag rounds over a 2-bit staged piece in shared "
-                         "memory; pieces > 196 kb: shared-memory bitmap passes; k = 13: L2 bitmap; k > 13: hash)",
-               "bound": "issue+barrier (one CTA per piece: ~43 k warp-instructions and ~14 barriers per 15 kb piece; "
-                        "ncu: issue slots 52 % busy, 29 % of stall samples on barriers)",
-               "achieved": kept_bases / (kmer_ms / 1e3) / 1e9 if kmer_ms > 0 else 0.0, "peak": None,
-               "unit": "Ginserts/s", "frac": None, "traffic": None, "work": "1 insert per kept base",
-               "ms": kmer_ms, "share_of_step": kmer_ms / step_ms if step_ms else None}
+                "ms": clean_ms, "share_of_step": share(clean_ms)}
+    # K4: no memory roofline applies (1 B/base of HBM traffic is < 5 % of peak); the kernel is bound by instruction
+    # issue.  Peak = inserts/s if every issue slot of the GPU issued one of the kernel's own instructions each cycle:
+    # 4 slots x 148 SMs x clock / (warp-instructions per insert, from the ncu capture in profiles/).
+    kmer_inserts = kept_bases / (kmer_ms / 1e3) / 1e9 if kmer_ms > 0 else 0.0
+    k4_prof = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_kmer_issue.json")) as f:
+            k4_prof = json.load(f)
+    except Exception:
+        pass
+    wi = k4_prof.get("warp_instructions_per_insert")
+    kmer_peak = 4 * 148 * sm_clock * 1e6 / wi / 1e9 if wi else None
+    rl_kmer = {"kernel": "k_kmer_tag16 (K4, k <= 12: owner-byte dense round + position-tag list rounds in shared memory, "
+                         "2 CTAs/SM, producer warps; pieces > 65 kb: k_kmer_smem; k = 13: L2 bitmap; k > 13: hash)",
+               "bound": "issue", "achieved": kmer_inserts, "peak": kmer_peak, "unit": "Ginserts/s",
+               "frac": kmer_inserts / kmer_peak if kmer_peak else None, "traffic": None,
+               "work": "1 set insert per kept base",
+               "peak_def": (f"4 issue slots x 148 SMs x {sm_clock:.0f} MHz / {wi} warp-instructions per insert "
+                            f"(ncu, {k4_prof.get('source')})") if wi else "no ncu capture committed",
+               "hbm_view": {"achieved_gbs": kmer_inserts, "frac_of_hbm": kmer_inserts / hbm_peak,
+                            "work": "1 B per kept base (SURVEY.md §8d)"},
+               "ms": kmer_ms, "share_of_step": share(kmer_ms)}
     # measured DRAM traffic per launch (one ncu --set full capture of this same command, committed
     # under profiles/); only valid for the workload it was captured on
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tr = json.load(f)
-        if tr.get("config") == cfg and tr.get("reads_per_gpu") == n_reads:
+        if tr.get("config") == cfg and tr.get("reads_per_gpu") == local_reads and len(batches) == 1:
             rl_mid["traffic"] = tr["k_mid_scan"]["dram_bytes"]
             mid_all = lens - 2 * E
             qmin = min(len(a) for a in params.adapters)
             # 1 B per middle-window column of the reads that pass -q/-Q; one pass serves both adapters
             rl_mid["algorithmic_bytes"] = int(int(mid_all[mid_all >= qmin].sum()) * active_frac)
             rl_raw["traffic"] = tr["k_scan_tiles_raw"]["dram_bytes"]
-            rl_raw["algorithmic_bytes"] = 2 * n_bases
+            rl_raw["algorithmic_bytes"] = 2 * local_bases
             rl_clean["traffic"] = tr["k_scan_tiles_clean"]["dram_bytes"]
     except Exception:
         pass
@@ -594,28 +837,20 @@ def main():
     roofline = by_stage[dominant]
     roofline_kernels = {k: v for k, v in by_stage.items() if k != dominant and v["ms"] > 0}
     roofline_kernels["stage_ms_per_step"] = {k: v / args.steps for k, v in stage_sum.items()}
+    roofline_kernels["stage_ms_note"] = ("from one extra pass with a single batch in flight (sum over the batches: "
+                                         f"{serial_ms:.3f} ms); the timed steps keep two batches in flight, whose stages overlap")
 
     line = {
         "metric": "filtered Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64",
+        "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u8/u64",
         "data": "synthetic",
-        "config": {"workload": workload_name(cfg, n_reads), "cli": " ".join(cli),
-                   "reads_per_gpu": n_reads, "bases_per_gpu": n_bases,
-                   "adapters": [a.decode() for a in params.adapters],
-                   "head_trim": params.head_trim, "tail_trim": params.tail_trim,
-                   "l2": "inputs (2 B/base, >= 0.5 GB per launch) are larger than the 126 MB L2",
-                   "timing": "CUDA events on the library stream around the K1..K5 sequence, max over ranks"},
-        "e2e_bytes": {"value": e2e_value, "unit": "Gbases/s", "h2d_bytes_per_step": int(2 * n_bases + 8 * (n_reads + len(sub))) * world,
-                "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2,
-                "input_format": "byte bases + Phred bytes + offsets in pinned host memory (tgsf_submit)"},
-        "e2e": {"value": e2e_packed_value, "unit": "Gbases/s",
-                       "h2d_bytes_per_step": int(pk_off[-1] + n_bases + 8 * (n_reads + len(sub))) * world,
-                       "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": len(sub), "slots": 2,
-                       "input_format": "2-bit packed bases + Phred bytes + offsets in pinned host memory "
-                                       "(tgsf_submit_packed, the path src/TGSFilter.cpp uses); packing is host "
-                                       "parser work outside the timed region",
-                       "host_pack_gbases_per_s_per_thread": pack_gbs},
+        "config": static_config(cfg, n_total, strong),
+        "workload_detail": {"reads_this_rank": local_reads, "bases_this_rank": local_bases, "bases_all_ranks": int(total_bases),
+                            "batches_this_rank": len(batches), "adapters": [a.decode() for a in params.adapters],
+                            "head_trim": params.head_trim, "tail_trim": params.tail_trim,
+                            "timing": "device clock: first kernel start to last kernel end of the step's batches "
+                                      "(+ counter allreduce in strong mode), max over ranks"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -625,20 +860,37 @@ def main():
         "allreduce_ms": allreduce_ms,
         "drop_info_per_step": [int(x) // args.steps for x in drop],
     }
+    if want_e2e:
+        nsub = len(sub)
+        line["e2e_bytes"] = {"value": e2e_value, "unit": "Gbases/s",
+                             "h2d_bytes_per_step": int(2 * local_bases + 8 * (local_reads + nsub)) * world,
+                             "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": nsub, "slots": 2,
+                             "input_format": "byte bases + Phred bytes + offsets in pinned host memory (tgsf_submit)"}
+        line["e2e"] = {"value": e2e_packed_value, "unit": "Gbases/s",
+                       "h2d_bytes_per_step": int(pk_total + local_bases + 8 * (local_reads + nsub)) * world,
+                       "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": nsub, "slots": 2,
+                       "input_format": "2-bit packed bases + Phred bytes + offsets in pinned host memory "
+                                       "(tgsf_submit_packed, the path src/TGSFilter.cpp uses); packing is host "
+                                       "parser work outside the timed region",
+                       "host_pack_gbases_per_s_per_thread": pack_gbs}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_CLI):
-        tmpdir = tempfile.mkdtemp(prefix="tgsf_ref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        # the reference on the same dataset, once (bounded: at most ~5 Gbases, ~2 Gbases with -p)
+        tmpdir = tempfile.mkdtemp(prefix="tgsf_ref_", dir=shm_dir())
         try:
-            fq, nb = reference_sample_fastq(cfg, args.sample_reads)
+            cap_bases = 2.0e9 if "-p" in cli else 5.0e9
+            mean_len = local_bases / max(local_reads, 1)
+            cap_reads = 0 if local_bases <= cap_bases else int(cap_bases / mean_len)
             fq_path = os.path.join(tmpdir, "sample.fq")
-            with open(fq_path, "wb") as f:
-                f.write(fq)
+            del batches[1:]
+            r_reads, r_bases, gen = write_reference_fastq(cfg, plan, fq_path, args.sample_reads or cap_reads)
             threads = ref_threads()
-            v, secs = time_reference(cfg, fq_path, nb, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "Gbases/s", "cores": threads, "kind": "reference",
-                                    "sample": f"first {args.sample_reads} reads of the config-{cfg} generator "
-                                              f"({nb} bases) through the unmodified reference CLI, -t {threads}, "
-                                              f"FASTQ on tmpfs, {secs:.1f} s"}
+            secs = run_reference_once(cfg, fq_path, threads)
+            whole = r_reads == local_reads
+            line["cpu_baseline"] = {"value": r_bases / secs / 1e9, "unit": "Gbases/s", "cores": threads, "kind": "reference",
+                                    "sample": f"{'the whole dataset' if whole else 'the first ' + str(r_reads) + ' reads'} "
+                                              f"({r_reads} reads, {r_bases} bases) through the unmodified reference CLI, "
+                                              f"-t {threads}, FASTQ on tmpfs, one run of {secs:.1f} s"}
         except Exception as exc:  # keep the GPU line even if the CPU leg fails
             line["cpu_baseline"] = {"value": None, "unit": "Gbases/s", "cores": 0, "kind": "reference",
                                     "sample": f"failed: {exc}"}

@@ -139,6 +139,10 @@ const char *tgsf_last_error(void);
 int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out);
 int tgsf_destroy(tgsf_ctx *ctx);
 
+/* Number of CUDA devices this process can use (0 and TGSF_ERR_CUDA without a driver / device).  The
+ * host uses it to validate --gpus and, in the tests, to place several contexts on one device. */
+int tgsf_device_count(int *count);
+
 /* Pinned host memory for batch buffers (the packer of T.cpp:1845-1916's replacement fills these). */
 int tgsf_host_alloc(void **ptr, size_t bytes);
 int tgsf_host_free(void *ptr);
@@ -197,6 +201,12 @@ int tgsf_last_timing(tgsf_ctx *ctx, float *kernel_ms, float *total_ms);
 #define TGSF_STAGE_KMER 5        /* K4 */
 #define TGSF_STAGE_CLEAN 6       /* K1 over the kept pieces + clean decisions + clean 5'/3' */
 int tgsf_last_stage_ms(tgsf_ctx *ctx, float *out, int n);
+
+/* Device-clock interval of the batch retired by the last tgsf_collect, in ms since the context was
+ * created: [start_ms, end_ms] brackets its kernels (not the copies).  Batches in different slots run
+ * on different streams and may overlap on the GPU, so the device time of a group of batches is
+ * max(end) - min(start), not the sum of tgsf_last_timing (bench.py measures a step this way). */
+int tgsf_last_span(tgsf_ctx *ctx, float *start_ms, float *end_ms);
 
 /* Replaces: the per-thread accumulators of TGSFilterTask and their merge (T.cpp:1796-1806,
  * 3208-3213).  Cumulative since create / the last reset.  All batches must have been collected. */

@@ -513,11 +513,14 @@ int main(int argc, char **argv) {
     std::unique_ptr<ingest::ParallelReader> preader; // plain files: parallel chunk parser
     auto next_parsed = [&]() { return preader ? preader->pop() : parsed.pop(); };
     std::atomic<bool> reader_stop{false};
+    // Leaving main while the reader / writer threads are joinable would call std::terminate; every exit after this point
+    // (errors, -A) therefore goes the way the normal end of main goes: flush, then _exit without tearing anything down.
+    auto quit = [&](int code) -> int { std::cout.flush(); cerr.flush(); fflush(nullptr); _exit(code); return code; };
     std::function<bool()> start_readers;
     bool two_pass = false; // the pre-pass sample did not fit the buffer budget: the main pass re-reads the input
     const bool stream_input = P.Filter || P.OnlyQC;
     if (stream_input) {
-        { gzFile probe = gzopen(P.InFile.c_str(), "rb"); if (!probe) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; } gzclose(probe); }
+        { gzFile probe = gzopen(P.InFile.c_str(), "rb"); if (!probe) { cerr << "Error: Failed to open file: " << P.InFile << endl; return quit(1); } gzclose(probe); }
         // CUDA context creation (0.4-0.7 s warm, 1.3 s+ for the first process on a box) overlaps the parsing;
         // TGSF_INIT_FIRST=1 creates it before the parser threads start (measured: no faster)
         const bool init_first = getenv("TGSF_INIT_FIRST") != nullptr;
@@ -534,7 +537,7 @@ int main(int argc, char **argv) {
             reader = std::thread(ingest::reader_main, P.InFile, has_qual, batch_bases, &parsed, &batch_pool, &reader_stop, sambam);
             return true;
         };
-        if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
+        if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return quit(1); }
         if (!init_first) warm_up();
         while (!input_done && seqNum < maxSeq) {
             std::unique_ptr<ingest::RawBatch> rb = next_parsed();
@@ -575,11 +578,11 @@ int main(int argc, char **argv) {
                 reader.join();
             }
             input_done = false;
-            if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
+            if (!start_readers()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return quit(1); }
         }
     } else { // -F: only the sample is needed here; DownSampleTask reads the file itself
         FastxReader rd(P.InFile);
-        if (!rd.ok()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return 1; }
+        if (!rd.ok()) { cerr << "Error: Failed to open file: " << P.InFile << endl; return quit(1); }
         string name, seq, qual;
         while (rd.read(name, seq, qual)) {
             int L = (int)seq.size();
@@ -674,7 +677,7 @@ int main(int argc, char **argv) {
             cerr << "INFO: 3' adapter: " << a3 << endl;
             cerr << "INFO: mean depth of 5' adapter: " << d5 << endl;
             cerr << "INFO: mean depth of 3' adapter: " << d3 << endl;
-            if (P.ONLYAD) return 0;
+            if (P.ONLYAD) return quit(0);
             if (!a5.empty()) { add_adapter(a5); add_adapter(rev_comp(a5)); }
             if (!a3.empty()) { add_adapter(a3); add_adapter(rev_comp(a3)); }
             if (a5.empty() && a3.empty()) {
@@ -716,8 +719,17 @@ int main(int argc, char **argv) {
     tp.adapter_len = alen.data();
     tp.n_slots = 2;
     std::vector<tgsf_ctx *> ctx((size_t)P.gpus, nullptr);
+    int n_dev = 0;
+    if (tgsf_device_count(&n_dev) != TGSF_OK || n_dev < 1) die_tgsf("tgsf_device_count");
+    // TGSF_SHARE_DEVICES=1: more contexts than devices are placed round-robin (context g on device g % devices), so
+    // the multi-GPU path (batch dealing, per-context counters, tgsf_allreduce) can run on a single-GPU box
+    const bool share_dev = getenv("TGSF_SHARE_DEVICES") != nullptr;
+    if (P.gpus > n_dev && !share_dev) {
+        cerr << "Error: --gpus " << P.gpus << " but only " << n_dev << " CUDA device(s) are visible" << endl;
+        return quit(1);
+    }
     for (int g = 0; g < P.gpus; g++)
-        if (tgsf_create(g, &tp, &ctx[(size_t)g]) != TGSF_OK) die_tgsf("tgsf_create");
+        if (tgsf_create(g % n_dev, &tp, &ctx[(size_t)g]) != TGSF_OK) die_tgsf("tgsf_create");
 
     tlog("tgsf_create", T_ph.lap());
     // ---- main pass -----------------------------------------------------------------------------------
@@ -726,10 +738,10 @@ int main(int argc, char **argv) {
         string prefix = P.InFile;
         tmpPath = prefix + ".tmp." + std::to_string((long)getpid()) + (P.Outfq == 0 ? ".fa" : ".fq");
         out = fopen(tmpPath.c_str(), "wb");
-        if (!out) { cerr << "Error: Failed to open file: " << tmpPath << endl; return 1; }
+        if (!out) { cerr << "Error: Failed to open file: " << tmpPath << endl; return quit(1); }
     } else if (!P.OnlyQC && !P.OutFile.empty()) {
         out = fopen(P.OutFile.c_str(), "w+b"); // read-write: the plain writer maps the file
-        if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
+        if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return quit(1); }
     }
     const bool gz_now = P.OUTGZ && !P.Downsample; // T.cpp:2022
     // pinned staging ring: what crosses PCIe (2-bit packed bases, Phred bytes); 2 slots per GPU
@@ -1145,7 +1157,7 @@ int main(int argc, char **argv) {
         if ((int)inflight.size() == slots) retire(); // ring slot `cur` is the oldest one in flight
         t_retire += T_loop.lap();
         PinSlot &sl = ring[(size_t)cur];
-        if (!sl.reserve((size_t)nb + 64)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
+        if (!sl.reserve((size_t)nb + 64)) { cerr << "Error: out of pinned host memory" << endl; return quit(1); }
         // pack the bases (2 bits) and copy the qualities into the pinned slot on a few threads: the ranges are
         // multiples of 32 bases, their exception lists are concatenated with the range offset added
         uint64_t ne = 0;
@@ -1261,7 +1273,7 @@ int main(int argc, char **argv) {
         FILE *fout = stdout;
         if (!P.OutFile.empty()) {
             fout = fopen(P.OutFile.c_str(), "wb");
-            if (!fout) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return 1; }
+            if (!fout) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return quit(1); }
         }
         // .gz: one member per record, compressed in chunks of ~64 MB by -t threads (same strategy rule as the main pass)
         std::vector<string> gz_pend;
@@ -1360,7 +1372,7 @@ int main(int argc, char **argv) {
                 if (P.Outfq == 1) { rec += '@'; rec += name; rec += '\n'; rec += seq; rec += "\n+\n"; rec += qual; rec += '\n'; }
                 else { rec += '>'; rec += name; rec += '\n'; rec += seq; rec += '\n'; }
                 emit(rec.data(), rec.size());
-                if (!qb.add(name, seq, qual, dqual)) { cerr << "Error: out of pinned host memory" << endl; return 1; }
+                if (!qb.add(name, seq, qual, dqual)) { cerr << "Error: out of pinned host memory" << endl; return quit(1); }
                 if (qb.used >= P.batch_bases) flush();
             }
             flush();

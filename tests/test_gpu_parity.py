@@ -652,8 +652,8 @@ def test_host_cli_two_gpus_equals_one(cfg, args, monkeypatch):
     """--gpus 2: batches alternate between two contexts, counters merged by tgsf_allreduce; records (in
     input order), INFO lines and the report must equal the single-GPU run."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < 2:  # single-GPU lease: both contexts on device 0 (same host path, peer copy = local copy)
+        monkeypatch.setenv("TGSF_SHARE_DEVICES", "1")
     monkeypatch.setenv("TGSF_BATCH_MB", "1")  # many small batches, so both GPUs get work
     batch = synth.make_config(cfg, 600, max_len=40000)
     fq = batch.to_fastq()
@@ -830,3 +830,25 @@ def test_host_cli_bam_and_sam_input(monkeypatch):
     if ref_lib.available():
         r_rc, r_out, r_err, _ = ref_lib.run_cli(["-x", "ont", "-t", "1"], bam, in_name="in.bam")
         assert r_rc == 0 and r_out == out1 and _info(r_err) == _info(err1)
+
+
+@pytest.mark.parametrize("kind", ["plain", "gz", "bam"])
+def test_host_cli_adapter_identification_only(kind):
+    """-A: adapter identification only (T.cpp:3071-3098).  The run ends right after the pre-pass; with streamed
+    input (.gz, BAM) the ingest thread is still alive at that point and must not abort the process (exit 0, same
+    INFO lines as the reference)."""
+    import gzip
+    import bam_lib
+    import ref_lib
+    fq = synth.make_config(2, 300, max_len=40000, with_names=False).to_fastq()
+    data, name = fq, "in.fq"
+    if kind == "gz":
+        data, name = gzip.compress(fq, 1), "in.fq.gz"
+    elif kind == "bam":
+        data, name = bam_lib.from_fastq(fq)[0], "in.bam"
+    rc, out, err = _run_host_cli(["-x", "ont", "-A"], data, in_name=name, out_name=None)
+    assert rc == 0, (rc, err[-500:])
+    assert any(l.startswith("INFO: 5' adapter:") for l in err.splitlines())
+    if ref_lib.available():
+        r_rc, _, r_err, _ = ref_lib.run_cli(["-x", "ont", "-A", "-t", "1"], data, in_name=name, out_name=None)
+        assert r_rc == 0 and _info(err) == _info(r_err)

@@ -112,8 +112,8 @@ ALIGN_RESULT_DTYPE = [("edit_distance", "<i4"), ("n_locations", "<i4"), ("align_
 
 # every symbol include/tgsf.h declares; tests check the built library exports all of them
 EXPORTED_SYMBOLS = (
-    "tgsf_version", "tgsf_last_error", "tgsf_create", "tgsf_destroy", "tgsf_host_alloc",
-    "tgsf_host_free", "tgsf_submit", "tgsf_submit_packed", "tgsf_pack_bases", "tgsf_submit_device", "tgsf_collect", "tgsf_collect_gz", "tgsf_last_timing", "tgsf_last_stage_ms",
+    "tgsf_version", "tgsf_last_error", "tgsf_create", "tgsf_destroy", "tgsf_device_count", "tgsf_host_alloc",
+    "tgsf_host_free", "tgsf_submit", "tgsf_submit_packed", "tgsf_pack_bases", "tgsf_submit_device", "tgsf_collect", "tgsf_collect_gz", "tgsf_last_timing", "tgsf_last_span", "tgsf_last_stage_ms",
     "tgsf_counter_layout_get", "tgsf_counters", "tgsf_counters_reset", "tgsf_counters_device",
     "tgsf_launch_count", "tgsf_allreduce", "tgsf_prepass", "tgsf_align_hw",
 )
@@ -138,6 +138,7 @@ def load() -> C.CDLL:
     lib.tgsf_last_error.argtypes = []
     lib.tgsf_create.argtypes = [C.c_int, C.POINTER(Params), C.POINTER(vp)]
     lib.tgsf_destroy.argtypes = [vp]
+    lib.tgsf_device_count.argtypes = [C.POINTER(C.c_int)]
     lib.tgsf_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
     lib.tgsf_host_free.argtypes = [vp]
     lib.tgsf_submit.argtypes = [vp, u8p, u8p, u64p, C.c_uint32]
@@ -147,6 +148,7 @@ def load() -> C.CDLL:
     lib.tgsf_collect.argtypes = [vp, vp, C.c_uint32, vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.tgsf_collect_gz.argtypes = [vp, vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_uint32, C.POINTER(C.c_uint32)]
     lib.tgsf_last_timing.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.tgsf_last_span.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.tgsf_last_stage_ms.argtypes = [vp, C.POINTER(C.c_float), C.c_int]
     lib.tgsf_counter_layout_get.argtypes = [vp, C.POINTER(CounterLayout)]
     lib.tgsf_counters.argtypes = [vp, u64p, C.c_uint32]

@@ -231,6 +231,8 @@ struct tgsf_ctx {
     u32 kmer16_list_cap = KMER16_LIST_CAP; // TGSF_KMER16_LIST_CAP=n: smaller pending list (tests of the retry path)
     float last_kernel_ms = 0, last_total_ms = 0;
     float last_stage_ms[TGSF_N_STAGES] = {};
+    cudaEvent_t ev_epoch = nullptr; // recorded at creation: origin of tgsf_last_span
+    float last_span_start = 0, last_span_end = 0;
 };
 
 namespace {
@@ -770,6 +772,12 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
     const int ns = params->n_slots > 0 ? params->n_slots : 2;
     c->slots.resize((size_t)ns);
     for (int i = 0; i < ns && rc == TGSF_OK; ++i) rc = slot_init(c->slots[(size_t)i]);
+    if (rc == TGSF_OK && (cudaEventCreate(&c->ev_epoch) != cudaSuccess ||
+                          cudaEventRecord(c->ev_epoch, c->slots[0].stream) != cudaSuccess ||
+                          cudaEventSynchronize(c->ev_epoch) != cudaSuccess)) {
+        set_err("epoch event: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = TGSF_ERR_CUDA;
+    }
     if (rc == TGSF_OK) {
         cudaError_t e1 = cudaFuncSetAttribute(k_scan_tiles_dyn<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
         cudaError_t e2 = cudaFuncSetAttribute(k_scan_tiles_dyn<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES);
@@ -804,9 +812,17 @@ int tgsf_destroy(tgsf_ctx *c) {
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (auto &s : c->slots) slot_release(s);
+    if (c->ev_epoch) cudaEventDestroy(c->ev_epoch);
     c->ads.release();
     c->counters.release();
     delete c;
+    return TGSF_OK;
+}
+
+int tgsf_device_count(int *count) {
+    if (!count) return TGSF_ERR_INVALID;
+    *count = 0;
+    CU(cudaGetDeviceCount(count));
     return TGSF_OK;
 }
 
@@ -1037,6 +1053,9 @@ int tgsf_collect(tgsf_ctx *c, tgsf_read_result *reads, uint32_t n_reads, tgsf_pi
     cudaEventElapsedTime(&t_ms, s.ev_start, s.ev_end);
     c->last_kernel_ms = k_ms + extra_ms;
     c->last_total_ms = t_ms + extra_ms;
+    cudaEventElapsedTime(&c->last_span_start, c->ev_epoch, s.ev_k0);
+    cudaEventElapsedTime(&c->last_span_end, c->ev_epoch, s.ev_k1);
+    c->last_span_end += extra_ms;
     for (int i = 0; i < TGSF_N_STAGES; ++i) {
         float ms = 0;
         cudaEventElapsedTime(&ms, s.ev_stage[i], s.ev_stage[i + 1]);
@@ -1080,6 +1099,13 @@ int tgsf_last_timing(tgsf_ctx *c, float *kernel_ms, float *total_ms) {
     if (!c) return TGSF_ERR_INVALID;
     if (kernel_ms) *kernel_ms = c->last_kernel_ms;
     if (total_ms) *total_ms = c->last_total_ms;
+    return TGSF_OK;
+}
+
+int tgsf_last_span(tgsf_ctx *c, float *start_ms, float *end_ms) {
+    if (!c) return TGSF_ERR_INVALID;
+    if (start_ms) *start_ms = c->last_span_start;
+    if (end_ms) *end_ms = c->last_span_end;
     return TGSF_OK;
 }
 

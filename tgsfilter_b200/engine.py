@@ -190,6 +190,12 @@ class FilterEngine:
         _capi.check(self._lib.tgsf_last_timing(self._ctx, C.byref(k), C.byref(t)), "tgsf_last_timing")
         return k.value, t.value
 
+    def last_span(self) -> Tuple[float, float]:
+        """[start, end] of the last collected batch's kernels on the device clock (ms since create)."""
+        a, b = C.c_float(0), C.c_float(0)
+        _capi.check(self._lib.tgsf_last_span(self._ctx, C.byref(a), C.byref(b)), "tgsf_last_span")
+        return a.value, b.value
+
     def last_stage_ms(self) -> dict:
         arr = (C.c_float * _capi.N_STAGES)()
         _capi.check(self._lib.tgsf_last_stage_ms(self._ctx, arr, _capi.N_STAGES), "tgsf_last_stage_ms")

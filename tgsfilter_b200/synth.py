@@ -62,22 +62,26 @@ class ReadBatch:
                          None if self.names is None else self.names[lo:hi])
 
 
+def write_fastq_to(f, bases: np.ndarray, quals: np.ndarray, offsets: np.ndarray, prefix: bytes = b"read") -> int:
+    """Concatenated arrays -> 4-line FASTQ records ``@<prefix><i>`` on an open binary file.  The per-base
+    copies happen inside ``write``; the Python loop only runs once per read.  Returns the bytes written."""
+    mb, mq = memoryview(bases), memoryview(quals)
+    off = np.asarray(offsets).astype(np.int64).tolist()
+    written = 0
+    for i in range(len(off) - 1):
+        s, e = off[i], off[i + 1]
+        written += f.write(b"@%s%d\n" % (prefix, i))
+        written += f.write(mb[s:e])
+        written += f.write(b"\n+\n")
+        written += f.write(mq[s:e])
+        written += f.write(b"\n")
+    return written
+
+
 def write_fastq(path: str, bases: np.ndarray, quals: np.ndarray, offsets: np.ndarray,
                 prefix: bytes = b"read") -> int:
-    """Concatenated arrays -> 4-line FASTQ file with records ``@<prefix><i>``.  The per-base copies
-    happen inside ``write``; the Python loop only runs once per read.  Returns the bytes written."""
-    mb, mq = memoryview(bases), memoryview(quals)
-    off = offsets.astype(np.int64).tolist()
-    written = 0
     with open(path, "wb", buffering=1 << 24) as f:
-        for i in range(len(off) - 1):
-            s, e = off[i], off[i + 1]
-            written += f.write(b"@%s%d\n" % (prefix, i))
-            written += f.write(mb[s:e])
-            written += f.write(b"\n+\n")
-            written += f.write(mq[s:e])
-            written += f.write(b"\n")
-    return written
+        return write_fastq_to(f, bases, quals, offsets, prefix)
 
 
 def pack_reads(seqs: List[bytes], quals: Optional[List[bytes]] = None,
