@@ -61,13 +61,13 @@ def batch_seed(cfg: int, rank: int, j: int) -> int:
     return SEED0 + cfg + 1000 * rank + 100000 * j
 
 
-def plan_batches(cfg: int, n_total: int, world: int, rank: int, strong: bool):
+def plan_batches(cfg: int, n_total: int, world: int, rank: int, strong: bool, split: int = 0):
     """[(global batch index, reads, seed)] this rank generates and processes."""
     if strong:
         nb = min(STRONG_BATCHES, n_total)
         sizes = [n_total // nb + (1 if j < n_total % nb else 0) for j in range(nb)]
         return [(j, sizes[j], batch_seed(cfg, 0, j)) for j in range(nb) if j % world == rank]
-    nb = max(1, math.ceil(n_total / SUB_READS))
+    nb = max(1, math.ceil(n_total / SUB_READS), split)
     sizes = [n_total // nb + (1 if j < n_total % nb else 0) for j in range(nb)]
     return [(j, sizes[j], batch_seed(cfg, rank, j)) for j in range(nb)]
 
@@ -391,7 +391,7 @@ def run_reference_arm(args):
         return 0
     threads = ref_threads()
     budget = float(os.environ.get("TGSF_REF_BUDGET_S", "600"))
-    plan = plan_batches(cfg, n_total, 1, 0, strong)
+    plan = plan_batches(cfg, n_total, 1, 0, strong, args.split)
     tmpdir = tempfile.mkdtemp(prefix="tgsf_ref_", dir=shm_dir())
     t_begin = time.perf_counter()
     try:
@@ -446,6 +446,8 @@ def main():
     ap.add_argument("--strong", action="store_true", default=os.environ.get("TGSF_BENCH_STRONG", "") not in ("", "0"),
                     help="strong scaling: one dataset dealt to the ranks, counter allreduce inside the step; env TGSF_BENCH_STRONG=1")
     ap.add_argument("--reads", type=int, default=0, help="reads in the dataset (0 = the config's full size)")
+    ap.add_argument("--split", type=int, default=int(os.environ.get("TGSF_BENCH_SPLIT", "0")),
+                    help="weak mode: feed the dataset as at least this many batches (two are in flight at a time)")
     ap.add_argument("--sample-reads", type=int, default=0, help="CPU reference: cap the reads per step (0 = whole dataset / time budget)")
     ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -479,7 +481,7 @@ def main():
     cfg, strong = args.config, args.strong
     n_total = args.reads or CONFIG_READS[cfg]
     read_type = CONFIG_TYPE[cfg]
-    plan = plan_batches(cfg, n_total, world, rank, strong)
+    plan = plan_batches(cfg, n_total, world, rank, strong, args.split)
 
     # ---- resident batches + pinned host copies
     class B:
@@ -517,7 +519,7 @@ def main():
         # the CLI samples the first 100 000 usable reads of the FILE: take the leading batches of the dataset
         # until they hold that many reads (batches that live on other ranks are regenerated here just for this)
         lead, have = [], 0
-        full_plan = plan_batches(cfg, n_total, 1, 0, strong) if strong else plan
+        full_plan = plan_batches(cfg, n_total, 1, 0, strong, args.split) if strong else plan
         by_j = {b.j: b for b in batches}
         for j, n, seed in full_plan:
             if have >= 100_000:
@@ -618,26 +620,46 @@ def main():
                     nb = int(b.offsets[c] - b.offsets[a])
                     sub.append((b, int(b.offsets[a]), int(c - a), o_t, nb, pk_total))
                     pk_total += ((nb + 3) // 4 + 63) // 64 * 64
-        # 2-bit packed copy of every sub-batch (what the C++ host's parser produces with tgsf_pack_bases;
-        # the synthetic bases are pure upper-case ACGT, so the exception list is empty)
+        # pinned staging for the 2-bit packed bases of every sub-batch; the packing itself (tgsf_pack_bases, the
+        # AVX2 packer src/TGSFilter.cpp uses) runs INSIDE the timed region on a pool of host threads
         h_packed = torch.empty(pk_total + 64, dtype=torch.uint8, pin_memory=True)
-        for b, s0, nr, o_t, nb, po in sub:
-            x = b.d_bases[s0:s0 + nb]
-            if nb % 4:
-                x = torch.cat([x, torch.full((4 - nb % 4,), 65, dtype=torch.uint8, device=device)])
-            code = (x >> 1) & 3
-            code = (code ^ (code >> 1)).view(-1, 4)          # A0 C1 G2 T3
-            pk = code[:, 0] | (code[:, 1] << 2) | (code[:, 2] << 4) | (code[:, 3] << 6)
-            h_packed[po:po + pk.numel()].copy_(pk)
-            del x, code, pk
         torch.cuda.synchronize()
     d2h_bytes = 0
+
+    import ctypes
+    from concurrent.futures import ThreadPoolExecutor
+    lib = _capi.load()
+    host_cores = os.cpu_count() or 2
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    pack_threads = max(1, min(12, (host_cores - local_world) // max(local_world, 1)))
+    if os.environ.get("TGSF_BENCH_PACK_THREADS"):
+        pack_threads = max(1, int(os.environ["TGSF_BENCH_PACK_THREADS"]))
+    pack_seconds = [0.0]
+    pool = ThreadPoolExecutor(pack_threads)
+
+    def pack_sub(b, s0, nb, po):
+        """bases[s0 : s0 + nb] -> 2-bit codes at h_packed[po ...], in pack_threads ranges that are multiples of 32 bases
+        (the synthetic bases are pure upper-case ACGT: a non-empty exception list is an error here)."""
+        src, dst = b.h_bases.data_ptr() + s0, h_packed.data_ptr() + po
+        per = ((nb + pack_threads - 1) // pack_threads + 31) // 32 * 32
+
+        def one(lo):
+            ne = ctypes.c_uint64(0)
+            n = min(per, nb - lo)
+            rc = lib.tgsf_pack_bases(src + lo, n, dst + lo // 4, None, None, 0, ctypes.byref(ne))
+            return rc, ne.value
+        tq = time.perf_counter()
+        for rc, ne in pool.map(one, range(0, nb, per)):
+            if rc != 0 or ne:
+                raise RuntimeError(f"tgsf_pack_bases: status {rc}, {ne} exceptions")
+        pack_seconds[0] += time.perf_counter() - tq
 
     def step_e2e_packed():
         nonlocal d2h_bytes
         d2h = 0
         inflight = 0
         for b, s0, nr, o_t, nb, po in sub:
+            pack_sub(b, s0, nb, po)  # overlaps the H2D copy and the kernels of the previous sub-batch
             if inflight == 2:
                 r, pcs = eng.collect()
                 d2h += r.nbytes + pcs.nbytes
@@ -720,17 +742,18 @@ def main():
     pack_gbs = None
     if want_e2e:
         e2e_s = timed_wall(step_e2e_bytes, args.steps)
+        pack_seconds[0] = 0.0
         e2e_packed_s = timed_wall(step_e2e_packed, args.steps)
+        pack_s_per_step = pack_seconds[0] / args.steps
         e2e_value = total_bases * args.steps / e2e_s / 1e9
         e2e_packed_value = total_bases * args.steps / e2e_packed_s / 1e9
         # host packer speed (one thread), for context
-        import ctypes
         b0 = batches[0]
         nb_probe = min(b0.n_bases, 256 << 20)
         probe_out = np.empty(nb_probe // 4 + 16, dtype=np.uint8)
         ne = ctypes.c_uint64(0)
         tp0 = time.perf_counter()
-        _capi.load().tgsf_pack_bases(b0.h_bases.data_ptr(), nb_probe, probe_out.ctypes.data, None, None, 0, ctypes.byref(ne))
+        lib.tgsf_pack_bases(b0.h_bases.data_ptr(), nb_probe, probe_out.ctypes.data, None, None, 0, ctypes.byref(ne))
         pack_gbs = nb_probe / (time.perf_counter() - tp0) / 1e9
 
     # ---- final counter allreduce over NVLink (weak mode: outside the timed region; reported)
@@ -862,17 +885,24 @@ def main():
     }
     if want_e2e:
         nsub = len(sub)
-        line["e2e_bytes"] = {"value": e2e_value, "unit": "Gbases/s",
-                             "h2d_bytes_per_step": int(2 * local_bases + 8 * (local_reads + nsub)) * world,
-                             "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": nsub, "slots": 2,
-                             "input_format": "byte bases + Phred bytes + offsets in pinned host memory (tgsf_submit)"}
-        line["e2e"] = {"value": e2e_packed_value, "unit": "Gbases/s",
-                       "h2d_bytes_per_step": int(pk_total + local_bases + 8 * (local_reads + nsub)) * world,
-                       "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": nsub, "slots": 2,
-                       "input_format": "2-bit packed bases + Phred bytes + offsets in pinned host memory "
-                                       "(tgsf_submit_packed, the path src/TGSFilter.cpp uses); packing is host "
-                                       "parser work outside the timed region",
-                       "host_pack_gbases_per_s_per_thread": pack_gbs}
+        e2e_b = {"value": e2e_value, "unit": "Gbases/s",
+                 "h2d_bytes_per_step": int(2 * local_bases + 8 * (local_reads + nsub)) * world,
+                 "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": nsub, "slots": 2,
+                 "input_format": "byte bases + Phred bytes + offsets in pinned host memory (tgsf_submit): nothing to prepare "
+                                 "on the host, 2 B/base over PCIe"}
+        e2e_p = {"value": e2e_packed_value, "unit": "Gbases/s",
+                 "h2d_bytes_per_step": int(pk_total + local_bases + 8 * (local_reads + nsub)) * world,
+                 "d2h_bytes_per_step": int(d2h_bytes) * world, "chunks": nsub, "slots": 2,
+                 "input_format": "byte bases + Phred bytes + offsets in pinned host memory; the bases are packed to 2 bits "
+                                 f"INSIDE the timed region by {pack_threads} host threads per rank (tgsf_pack_bases, the packer "
+                                 "src/TGSFilter.cpp uses), then tgsf_submit_packed: 1.25 B/base over PCIe",
+                 "pack_threads_per_rank": pack_threads, "host_cores": host_cores,
+                 "host_pack_ms_per_step": pack_s_per_step * 1e3, "wall_ms_per_step": e2e_packed_s / args.steps * 1e3,
+                 "host_pack_gbases_per_s_per_thread": pack_gbs}
+        # the host picks the feed that is faster on the box it runs on: packing pays while there are host cores to spare
+        best, other = (e2e_p, e2e_b) if e2e_packed_value >= e2e_value else (e2e_b, e2e_p)
+        line["e2e"] = best
+        line["e2e_other_feed"] = other
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_CLI):
         # the reference on the same dataset, once (bounded: at most ~5 Gbases, ~2 Gbases with -p)

@@ -31,8 +31,8 @@ extern "C" {
 
 #define TGSF_DROPINFO_N 17      /* DropInfo[17], T.cpp:1776, index meaning T.cpp:3216-3230 */
 #define TGSF_QUAL_HIST_N 256    /* raw/cleanDiffQualReadsBases[256], T.cpp:1777-1778 */
-#define TGSF_MAX_ADAPTERS 64    /* size of the global `adapters` set (T.cpp:1324) we accept */
-#define TGSF_MAX_ADAPTER_LEN 256 /* 4 x 64-bit Myers words */
+#define TGSF_MAX_ADAPTERS 65536 /* size of the global `adapters` set (T.cpp:1324) we accept; the work arrays grow with it */
+#define TGSF_MAX_ADAPTER_LEN 2048 /* 32 x 64-bit Myers words (1-4 words: exact count in registers; longer: 8, 16 or 32) */
 #define TGSF_LIB_ADAPTERS 22    /* adapterLib, T.cpp:2969-2991 */
 
 /* tgsf_params.flags */

@@ -30,6 +30,7 @@
 #include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -620,8 +621,11 @@ int main(int argc, char **argv) {
         }
     }
 
-    std::vector<string> adapters; // the global `adapters` set (T.cpp:1324); order is irrelevant
-    auto add_adapter = [&](const string &a) { if (std::find(adapters.begin(), adapters.end(), a) == adapters.end()) adapters.push_back(a); };
+    std::vector<string> adapters; // the global `adapters` set (T.cpp:1324); the order is irrelevant for the results
+    // ... but Get_adapters prints the set in std::unordered_set iteration order (T.cpp:2937-2940): the same container with the
+    // same insertions (same libstdc++ hash and rehash policy) reproduces that order for the `input adapter` lines
+    std::unordered_set<string> adapter_set;
+    auto add_adapter = [&](const string &a) { if (adapter_set.insert(a).second) adapters.push_back(a); };
     if (P.Filter) {
         std::vector<int32_t> bn5((size_t)checkLen * 4), bn3((size_t)checkLen * 4);
         std::vector<int64_t> m5(TGSF_LIB_ADAPTERS, 0), m3(TGSF_LIB_ADAPTERS, 0);
@@ -652,7 +656,7 @@ int main(int argc, char **argv) {
             string name, seq, qual;
             while (ar.read(name, seq, qual)) { add_adapter(seq); add_adapter(rev_comp(seq)); }
             int num = 0;
-            for (const string &a : adapters) cerr << "INFO: input adapter " << ++num << " :" << a << endl;
+            for (const string &a : adapter_set) cerr << "INFO: input adapter " << ++num << " :" << a << endl;
         } else { // tail of adapterSearch (T.cpp:1178-1208) + selection (T.cpp:3081-3125)
             float minSim = P.MidSim;
             if (minSim < 0.9) minSim = 0.9;

@@ -852,3 +852,133 @@ def test_host_cli_adapter_identification_only(kind):
     if ref_lib.available():
         r_rc, _, r_err, _ = ref_lib.run_cli(["-x", "ont", "-A", "-t", "1"], data, in_name=name, out_name=None)
         assert r_rc == 0 and _info(err) == _info(r_err)
+
+
+def _long_pairs(rng, n, q_lo, q_hi):
+    a = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs = []
+    for i in range(n):
+        ql = int(rng.integers(q_lo, q_hi + 1))
+        alpha = a if i % 4 else a[:2]
+        q = alpha[rng.integers(0, len(alpha), ql)].tobytes()
+        mode = i % 3
+        if mode == 0:
+            t = alpha[rng.integers(0, len(alpha), int(rng.integers(1, 2 * ql)))].tobytes()
+        elif mode == 1:
+            t = (alpha[rng.integers(0, len(alpha), int(rng.integers(0, 300)))].tobytes()
+                 + synth.mutate(q, float(rng.random() * 0.25), rng)
+                 + alpha[rng.integers(0, len(alpha), int(rng.integers(0, 300)))].tobytes()) or b"A"
+        else:
+            t = (q[:max(1, ql // 4)] * 9)[:int(rng.integers(1, 2 * ql))]
+        k = [-1, ql, max(0, ql - 3), int(ql * 0.1) + 1, int(ql * 0.3), int(rng.integers(0, ql + 1))][i % 6]
+        pairs.append((q, t, k))
+    return pairs
+
+
+def test_align_long_queries_vs_oracle_and_edlib():
+    """Adapters longer than 256 bp (5..32 Myers words; the library runs them with 8, 16 or 32 words): tgsf_align_hw
+    against the oracle's plain DP and, where the reference build is present, against the real edlibAlign
+    (E.cpp:141-296 has no length limit) for queries up to 2 000 bp."""
+    import ref_lib
+    rng = np.random.default_rng(77)
+    pairs = (_long_pairs(rng, 120, 257, 512) + _long_pairs(rng, 90, 513, 1024) + _long_pairs(rng, 60, 1025, 2000)
+             + _long_pairs(rng, 12, 2040, 2048))
+    out = align_hw(pairs)
+    for p, r in zip(pairs, out):
+        o, _ = oracle_lib.align_hw(*p)
+        for f in ("edit_distance", "n_locations", "align_len", "first_start", "first_end",
+                  "last_start", "last_end", "loc_hash"):
+            assert int(r[f]) == (o[f] & 0xffffffff if f == "loc_hash" else o[f]), (f, len(p[0]), len(p[1]), p[2])
+    if ref_lib.available():
+        ref = ref_lib.edlib_batch(pairs)
+        hirschberg = 0
+        for p, r, (d, alen, locs) in zip(pairs, out, ref):
+            assert int(r["edit_distance"]) == d and int(r["n_locations"]) == len(locs), (len(p[0]), len(p[1]), p[2])
+            # edlib switches from the traceback to Hirschberg's divide and conquer when the stored matrix of the
+            # located alignment would reach 1 MiB (E.cpp:1194-1215); that split picks other optimal paths in ties, so
+            # only there the alignment LENGTH may differ (library and oracle implement the traceback; DESIGN.md §7)
+            tl = locs[0][1] - locs[0][0] + 1 if locs else 0
+            big = (20 * ((len(p[0]) + 63) // 64)) * tl + 8 * tl >= 1 << 20
+            hirschberg += big
+            if not big:
+                assert int(r["align_len"]) == alen, (len(p[0]), len(p[1]), p[2])
+            if locs:
+                assert (int(r["first_start"]), int(r["first_end"])) == locs[0]
+                assert (int(r["last_start"]), int(r["last_end"])) == locs[-1]
+
+
+def _long_adapter_batch(adapters, n=160, seed=5):
+    """Reads with (mutated) copies of long adapters at the 5' end, the 3' end and in the middle."""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    seqs = []
+    for i in range(n):
+        ad = adapters[i % len(adapters)]
+        m = synth.mutate(ad, [0.0, 0.03, 0.08][i % 3], rng)
+        lo = max(3000, 4 * len(m) + 1500)
+        L = int(rng.integers(lo, lo + 5000))
+        s = bytearray(acgt[rng.integers(0, 4, L)].tobytes())
+        where = i % 5
+        if where == 0:
+            s[:len(m)] = m
+        elif where == 1:
+            s[L - len(m):] = m
+        elif where == 2:
+            p = int(rng.integers(len(m) + 500, L - 2 * len(m) - 500))
+            s[p:p + len(m)] = m
+        elif where == 3:
+            s[10:10 + len(m)] = m
+            p = int(rng.integers(len(m) + 800, L - 2 * len(m) - 500))
+            s[p:p + len(m)] = params_rev(m)
+        seqs.append(bytes(s[:L]))
+    quals = [bytes([30 + 33]) * len(s) for s in seqs]
+    return synth.pack_reads(seqs, quals, [b"r%d" % i for i in range(n)])
+
+
+def params_rev(b: bytes) -> bytes:
+    from tgsfilter_b200.params import rev_comp
+    return rev_comp(bytes(b))
+
+
+def test_long_adapters_per_read_vs_oracle():
+    """-a adapters of 300, 600 and 1 500 bp (8, 16 and 32 words) through the whole per-read path."""
+    rng = np.random.default_rng(9)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    ads = [acgt[rng.integers(0, 4, n)].tobytes() for n in (300, 600, 1500)]
+    adapters = []
+    for a in ads:
+        adapters += [a, params_rev(a)]
+    batch = _long_adapter_batch(ads, n=60)
+    params = FilterParams(min_len=500, min_q=0.0, qtype=33, adapters=adapters).apply_read_type("ont")
+    r, p, _ = _compare(params, batch)
+    assert (r["n_5p"] > 0).any() and (r["n_3p"] > 0).any() and (r["n_mid"] > 0).any()
+
+
+def test_many_adapters_per_read_vs_oracle():
+    """More than 64 adapters in the set (the round-1 cap)."""
+    rng = np.random.default_rng(10)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    ads = [acgt[rng.integers(0, 4, int(rng.integers(24, 70)))].tobytes() for _ in range(90)]
+    batch = _long_adapter_batch(ads, n=120, seed=6)
+    params = FilterParams(min_len=500, min_q=0.0, qtype=33, adapters=ads).apply_read_type("ont")
+    _compare(params, batch)
+
+
+def test_host_cli_long_adapter_file_vs_reference_cli(tmp_path):
+    """-a with a 600-bp adapter (T.cpp:1218-1322 takes any adapter file; edlib has no length cap)."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(12)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    ad = acgt[rng.integers(0, 4, 600)].tobytes()
+    batch = _long_adapter_batch([ad], n=200, seed=8)
+    fa = tmp_path / "adapters.fa"
+    fa.write_bytes(b">long\n" + ad + b"\n")
+    args = ["-x", "ont", "-a", str(fa)]
+    fq = batch.to_fastq()
+    r_rc, r_out, r_err, _ = ref_lib.run_cli(args + ["-t", "1"], fq)
+    h_rc, h_out, h_err = _run_host_cli(args, fq)
+    assert (h_rc, r_rc) == (0, 0), h_err
+    assert h_out == r_out and len(h_out) > 0
+    assert _info(h_err) == _info(r_err)

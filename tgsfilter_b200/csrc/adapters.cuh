@@ -95,18 +95,26 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
                const u32 *__restrict__ perm, const u32 *__restrict__ n_chunks_ptr,
                uint8_t *__restrict__ chunk_min,
                u32 *__restrict__ chunk_cnt, u64 *__restrict__ chunk_first,
-               u32 *__restrict__ best_mid) {
+               u32 *__restrict__ best_mid, u32 *__restrict__ work_ctr) {
     const u32 n_chunks = *n_chunks_ptr; // device-side total (chunk_off[n_reads])
-    extern __shared__ __align__(16) u64 s_peq[]; // [256][AP][NW] top-padded tables
+    extern __shared__ __align__(16) u64 s_peq_smem[]; // [256][AP][NW] top-padded tables
     DevAdapter A[AP];
 #pragma unroll
-    for (int x = 0; x < AP; ++x) {
-        A[x] = C.ad[M.a[x]];
-        const u64 *src = C.peq_pool + A[x].peq_off;
-        for (int i = threadIdx.x; i < 256 * NW; i += MID_THREADS)
-            s_peq[(i / NW) * (AP * NW) + x * NW + (i % NW)] = src[i];
+    for (int x = 0; x < AP; ++x) A[x] = C.ad[M.a[x]];
+    // adapters > 256 bp (NW > 4, always launched one per thread) read their table from global memory / L1: 256 x NW
+    // words do not fit the shared memory of several resident CTAs, and they are rare
+    const u64 *s_peq = s_peq_smem;
+    if (NW > 4) {
+        s_peq = C.peq_pool + A[0].peq_off;
+    } else {
+#pragma unroll
+        for (int x = 0; x < AP; ++x) {
+            const u64 *src = C.peq_pool + A[x].peq_off;
+            for (int i = threadIdx.x; i < 256 * NW; i += MID_THREADS)
+                s_peq_smem[(i / NW) * (AP * NW) + x * NW + (i % NW)] = src[i];
+        }
+        __syncthreads();
     }
-    __syncthreads();
     constexpr int TS = AP * NW; // table stride per byte value (in u64)
     const u64 chunk_len = 1ull << M.chunk_shift;
     int halo = 0, qmin = 0x7fffffff;
@@ -117,8 +125,17 @@ k_mid_scan_dyn(DevBatch B, AdapterCtx C, MidScanArgs M, const ChunkEntry *__rest
     }
     const uint4 *__restrict__ b16 = (const uint4 *)B.bases;
 
-    for (u32 it = blockIdx.x * MID_THREADS + threadIdx.x; it < n_chunks;
-         it += gridDim.x * MID_THREADS) {
+    // Work is handed out dynamically, 32 consecutive entries of the length-descending order per warp and fetch
+    // (zeroed counter per launch): longest chunks first, and CTAs that become resident late (another batch's
+    // kernels occupied the SM when this launch started) simply take fewer chunks instead of stretching the tail.
+    const u32 lane = threadIdx.x & 31u;
+    for (;;) {
+        u32 it = 0;
+        if (lane == 0) it = atomicAdd(work_ctr, 32u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_chunks) break;
+        it += lane;
+        if (it >= n_chunks) continue; // (the warp's next fetch ends the loop)
         const u32 ci = perm[it]; // length-descending order: a warp's 32 chunks have the same length
         const ChunkEntry ce = chunks[ci];
         const u64 rs = B.offsets[ce.read];
@@ -358,13 +375,16 @@ __global__ void __launch_bounds__(RES_THREADS)
 k_ends(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
        const int *__restrict__ read_active, int *__restrict__ end_n, int *__restrict__ end_pos,
        u64 *scratch, u64 scratch_stride) {
-    extern __shared__ u64 s_tab[]; // hw | fw | rv | rvhw tables of adapter a
+    extern __shared__ u64 s_tab_smem[]; // hw | fw | rv | rvhw tables of adapter a (NW <= 4; longer adapters: global memory)
     const DevAdapter A = C.ad[a];
-    {
+    const u64 *s_tab = s_tab_smem;
+    if (NW > 4) {
+        s_tab = C.peq_pool + A.peq_off;
+    } else {
         const u64 *src = C.peq_pool + A.peq_off;
-        for (int i = threadIdx.x; i < 4 * 256 * NW; i += RES_THREADS) s_tab[i] = src[i];
+        for (int i = threadIdx.x; i < 4 * 256 * NW; i += RES_THREADS) s_tab_smem[i] = src[i];
+        __syncthreads();
     }
-    __syncthreads();
     AdapterTables T;
     T.hw = s_tab;
     T.fw = s_tab + 256 * NW;

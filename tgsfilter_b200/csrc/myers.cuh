@@ -23,15 +23,16 @@ struct Myers {
     int score;
 };
 
-// State "before column 0" of an HW scan in the top-padded layout.
+// State "before column 0" of an HW scan in the top-padded layout.  W = 64*NW - qlen wildcard rows (vertical
+// delta 0) sit below the query; W >= 64 when NW is a rounded-up word count (adapters > 256 bp run with
+// NW = 8, 16 or 32).
 template <int NW>
 static __device__ __forceinline__ void myers_init_hw(Myers<NW> &s, int qlen) {
-    const int W = 64 * NW - qlen; // 0..63
-    s.Pv[0] = (W == 0) ? ~0ull : (~0ull << W);
-    s.Mv[0] = 0;
+    const int W = 64 * NW - qlen;
 #pragma unroll
-    for (int w = 1; w < NW; ++w) {
-        s.Pv[w] = ~0ull;
+    for (int w = 0; w < NW; ++w) {
+        const int below = W - 64 * w; // wildcard rows in this word and above it
+        s.Pv[w] = below >= 64 ? 0ull : (below <= 0 ? ~0ull : (~0ull << below));
         s.Mv[w] = 0;
     }
     s.score = qlen;
@@ -50,7 +51,8 @@ static __device__ __forceinline__ void myers_init_plain(Myers<NW> &s, int qlen) 
 
 // One column.  HIN = horizontal delta entering the top row: 0 for HW (free leading gap), +1 for
 // SHW / NW.  TOPBIT: the query's bottom row is bit 63 of the last word (HW layout); otherwise it is
-// bit `lastbit` of the last word.  Same recurrences as calculateBlock (E.cpp:409-444).
+// row `lastbit` = qlen - 1 counted from bit 0 of word 0 (word lastbit >> 6, which is NW - 1 unless NW is a
+// rounded-up word count).  Same recurrences as calculateBlock (E.cpp:409-444).
 template <int NW, int HIN, bool TOPBIT>
 static __device__ __forceinline__ void myers_step(Myers<NW> &s, const u64 *__restrict__ eq,
                                                   int lastbit) {
@@ -65,16 +67,13 @@ static __device__ __forceinline__ void myers_step(Myers<NW> &s, const u64 *__res
         const u64 Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
         u64 Ph = Mv | ~(Xh | Pv);
         u64 Mh = Pv & Xh;
-        int hout;
-        if (w == NW - 1) {
-            if (TOPBIT) {
-                hout = (int)(Ph >> 63) - (int)(Mh >> 63);
-            } else {
-                hout = (int)((Ph >> lastbit) & 1ull) - (int)((Mh >> lastbit) & 1ull);
-            }
-            s.score += hout;
+        const int hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+        if (TOPBIT) {
+            if (w == NW - 1) s.score += hout;
+        } else if (NW <= 4) { // exact word count: the bottom row is in the last word
+            if (w == NW - 1) s.score += (int)((Ph >> (lastbit & 63)) & 1ull) - (int)((Mh >> (lastbit & 63)) & 1ull);
         } else {
-            hout = (int)(Ph >> 63) - (int)(Mh >> 63);
+            if (w == (lastbit >> 6)) s.score += (int)((Ph >> (lastbit & 63)) & 1ull) - (int)((Mh >> (lastbit & 63)) & 1ull);
         }
         Ph = (Ph << 1) | ((hin > 0) ? 1ull : 0ull);
         Mh = (Mh << 1) | hinNeg;
@@ -177,7 +176,7 @@ static __device__ u64 shw_start(const AdapterTables &T, const uint8_t *__restric
                                 u64 e, int d) {
     Myers<NW> s;
     myers_init_plain<NW>(s, T.qlen);
-    const int lastbit = (T.qlen - 1) & 63;
+    const int lastbit = T.qlen - 1;
     u64 avail = e - wlo + 1;
     int ncols = (int)min(avail, (u64)(T.qlen + d));
     int last = 0;
@@ -216,7 +215,7 @@ static __device__ int nw_traceback_len(const AdapterTables &T, const uint8_t *__
                                        u64 s0, u64 e0, u64 *scratch, u64 stride) {
     const int q = T.qlen;
     const int tl = (int)(e0 - s0 + 1);
-    const int lastbit = (q - 1) & 63;
+    const int lastbit = q - 1;
     const int REC = 2 * NW + 1;
     Myers<NW> s;
     myers_init_plain<NW>(s, q);

@@ -98,6 +98,8 @@ struct HBuf { // pinned host
     }
 };
 
+inline int round_nw(int nw);
+
 // Adapter tables on the device (shared by the context, the pre-pass and tgsf_align_hw).
 struct AdapterSet {
     std::vector<DevAdapter> host;
@@ -113,7 +115,7 @@ struct AdapterSet {
             DevAdapter &A = host[(size_t)a];
             memset(&A, 0, sizeof(A));
             A.qlen = len[a];
-            A.nw = (len[a] + 63) / 64;
+            A.nw = round_nw((len[a] + 63) / 64);
             A.peq_off = (u32)words;
             words += (size_t)4 * 256 * (size_t)std::max(A.nw, 1);
             if (A.qlen > 0) {
@@ -169,13 +171,27 @@ struct AdapterSet {
     void release() { d_ad.release(); d_peq.release(); }
 };
 
-// Per-thread traceback scratch: RES grid is fixed so that the scratch is bounded.
+// Per-thread traceback scratch (nw_traceback_len: one (2*nw+1)-word record per target column and thread).  The
+// resolve kernels run grid-stride loops, so the grid of a launch is chosen per adapter such that its column store
+// stays within a budget: the default 4 CTAs per SM for ordinary adapters, fewer for very long ones.
+#define TGSF_SCRATCH_BUDGET (2ull << 30)
 struct Scratch {
     DBuf buf;
-    u64 stride = 0;
-    int ensure(u64 threads, int max_cols, int max_nw) {
-        stride = threads;
-        return buf.ensure((size_t)threads * (size_t)max_cols * (size_t)(2 * max_nw + 1) * sizeof(u64));
+    static size_t per_thread(int cols, int nw) { return (size_t)cols * (size_t)(2 * nw + 1) * sizeof(u64); }
+    static int grid_for(int default_grid, int threads_per_cta, int cols, int nw) {
+        const u64 fit = TGSF_SCRATCH_BUDGET / ((u64)per_thread(cols, nw) * (u64)threads_per_cta);
+        return (int)std::max<u64>(1, std::min<u64>((u64)default_grid, fit));
+    }
+    // size for the largest launch over `ads` with `default_grid` CTAs of `threads_per_cta` threads
+    template <typename ADS>
+    int ensure(const ADS &ads, int default_grid, int threads_per_cta) {
+        size_t need = 0;
+        for (const auto &A : ads) {
+            if (A.qlen <= 0 || A.nw <= 0) continue;
+            const int cols = 2 * A.qlen + 2;
+            need = std::max(need, (size_t)grid_for(default_grid, threads_per_cta, cols, A.nw) * threads_per_cta * per_thread(cols, A.nw));
+        }
+        return buf.ensure(std::max<size_t>(need, 256));
     }
 };
 
@@ -204,7 +220,7 @@ struct Slot {
     DBuf read_active, piece_cnt, piece_begin, chunk_cnt, chunk_off, chunks, chunk_min, chunk_hits, chunk_first, chunk_perm, chunk_hist;
     int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
-    DBuf scan_tmp, kmer_bitmaps, kmer_long_list, gz_blob, gz_spans;
+    DBuf scan_tmp, kmer_bitmaps, kmer_long_list, mid_work, gz_blob, gz_spans;
     Scratch scratch;
     u32 pool_cap = 0, pieces_cap = 0, chunks_cap = 0, tiles_cap = 0;
     // host results
@@ -277,7 +293,7 @@ void slot_release(Slot &s) {
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
                     &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
-                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.kmer_long_list, &s.gz_blob, &s.gz_spans, &s.scratch.buf};
+                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.kmer_long_list, &s.mid_work, &s.gz_blob, &s.gz_spans, &s.scratch.buf};
     for (DBuf *b : bufs) b->release();
     s.h_res.release();
     s.h_pieces.release();
@@ -333,6 +349,7 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.pieces.ensure((size_t)s.pieces_cap * sizeof(tgsf_piece)));
     TRY(s.res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
     TRY(s.header.ensure(sizeof(DevHeader)));
+    TRY(s.mid_work.ensure((size_t)A * sizeof(u32))); // one work counter per k_mid_scan launch
     if (c->P.flags & TGSF_FLAG_GZ_BLOCKS) {
         // literal-only Huffman coding: <= 9/8 bytes per symbol on average, plus headers and padding per piece
         const u64 syms = n_bases * ((c->P.flags & TGSF_FLAG_GZ_FASTA) ? 1ull : 2ull);
@@ -344,10 +361,13 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.h_res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
     TRY(s.h_pieces.ensure(((size_t)n + 4096) * sizeof(tgsf_piece)));
     TRY(s.h_header.ensure(sizeof(DevHeader)));
-    const u64 res_threads = (u64)c->sm_count * 4 * RES_THREADS;
-    TRY(s.scratch.ensure(res_threads, c->ads.max_cols, c->ads.max_nw));
+    TRY(s.scratch.ensure(c->ads.host, c->sm_count * 4, RES_THREADS));
     return TGSF_OK;
 }
+
+// Myers word counts with an instantiation: the exact count up to 4 (adapters <= 256 bp, state in registers), then
+// 8, 16 and 32 (<= 2048 bp; the state of those lives mostly in local memory, they are rare and only have to be right).
+inline int round_nw(int nw) { return nw <= 4 ? nw : nw <= 8 ? 8 : nw <= 16 ? 16 : 32; }
 
 template <typename F>
 int for_nw(int nw, F f) {
@@ -356,6 +376,9 @@ int for_nw(int nw, F f) {
         case 2: return f(std::integral_constant<int, 2>());
         case 3: return f(std::integral_constant<int, 3>());
         case 4: return f(std::integral_constant<int, 4>());
+        case 8: return f(std::integral_constant<int, 8>());
+        case 16: return f(std::integral_constant<int, 16>());
+        case 32: return f(std::integral_constant<int, 32>());
         default: set_err("adapter longer than %d", TGSF_MAX_ADAPTER_LEN); return TGSF_ERR_INVALID;
     }
 }
@@ -471,13 +494,16 @@ int launch_head(tgsf_ctx *c, Slot &s) {
         const AdapterCtx AC = c->ads.ctx();
         const u32 *n_chunks_ptr = s.chunk_off.as<u32>() + n;
         const int res_grid = c->sm_count * 4;
-        // adapters with a live middle search, paired by word count: two per thread
-        for (int nw = 1; nw <= 4; ++nw) {
+        int mid_launch = 0;
+        CU(cudaMemsetAsync(s.mid_work.p, 0, (size_t)A * sizeof(u32), st));
+        // adapters with a live middle search, paired by word count: two per thread (long adapters: one)
+        for (int nw : {1, 2, 3, 4, 8, 16, 32}) {
             std::vector<int> grp;
             for (int a = 0; a < A; ++a)
                 if (c->ads.host[(size_t)a].nw == nw && c->ads.host[(size_t)a].k_mid > 0) grp.push_back(a);
-            for (size_t i = 0; i < grp.size(); i += 2) {
-                const bool pair = i + 1 < grp.size();
+            const size_t step = nw <= 4 ? 2 : 1;
+            for (size_t i = 0; i < grp.size(); i += step) {
+                const bool pair = step == 2 && i + 1 < grp.size();
                 MidScanArgs M;
                 M.a[0] = grp[i];
                 M.a[1] = pair ? grp[i + 1] : grp[i];
@@ -493,11 +519,16 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                         kern<<<c->sm_count * occ, MID_THREADS, smem, st>>>(
                             s.B, AC, M, s.chunks.as<ChunkEntry>(), s.chunk_perm.as<u32>(), n_chunks_ptr,
                             s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
-                            s.best_mid.as<u32>());
+                            s.best_mid.as<u32>(), s.mid_work.as<u32>() + mid_launch);
                     };
-                    if (pair) launch(k_mid_scan_dyn<NW, 2>, 256 * 2 * NW * sizeof(u64));
-                    else launch(k_mid_scan_dyn<NW, 1>, 256 * NW * sizeof(u64));
+                    if constexpr (NW <= 4) {
+                        if (pair) launch(k_mid_scan_dyn<NW, 2>, 256 * 2 * NW * sizeof(u64));
+                        else launch(k_mid_scan_dyn<NW, 1>, 256 * NW * sizeof(u64));
+                    } else {
+                        launch(k_mid_scan_dyn<NW, 1>, 0); // table read from global memory
+                    }
                     c->launches++;
+                    ++mid_launch;
                     return check_launch("k_mid_scan");
                 }));
             }
@@ -505,18 +536,20 @@ int launch_head(tgsf_ctx *c, Slot &s) {
         CU(cudaEventRecord(s.ev_stage[3], st));
         for (int a = 0; a < A; ++a) {
             const DevAdapter &Ah = c->ads.host[(size_t)a];
+            const int grid_a = Scratch::grid_for(res_grid, RES_THREADS, 2 * Ah.qlen + 2, Ah.nw);
+            const u64 stride_a = (u64)grid_a * RES_THREADS;
             TRY(for_nw(Ah.nw, [&](auto nwc) {
                 constexpr int NW = decltype(nwc)::value;
                 if (Ah.k_mid > 0) {
-                    k_mid_count<NW><<<res_grid, RES_THREADS, 0, st>>>(
+                    k_mid_count<NW><<<grid_a, RES_THREADS, 0, st>>>(
                         s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(), s.chunks_cap,
                         s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
-                        s.mid_n.as<u32>(), s.scratch.buf.as<u64>(), s.scratch.stride);
+                        s.mid_n.as<u32>(), s.scratch.buf.as<u64>(), stride_a);
                     c->launches++;
                 }
-                k_ends<NW><<<res_grid, RES_THREADS, 4 * 256 * NW * sizeof(u64), st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
+                k_ends<NW><<<grid_a, RES_THREADS, NW <= 4 ? 4 * 256 * NW * sizeof(u64) : 0, st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
                                                             s.end_n.as<int>(), s.end_pos.as<int>(),
-                                                            s.scratch.buf.as<u64>(), s.scratch.stride);
+                                                            s.scratch.buf.as<u64>(), stride_a);
                 c->launches++;
                 return check_launch("k3 resolve");
             }));
@@ -1236,17 +1269,19 @@ int tgsf_prepass(int device, const uint8_t *ends5p, const uint8_t *ends3p, uint3
         }
         if (rc == TGSF_OK) rc = ads.upload();
         if (rc == TGSF_OK) rc = d_maps.ensure((size_t)2 * n_lib * sizeof(long long));
-        const u64 threads = (u64)sms * 4 * RES_THREADS;
-        if (rc == TGSF_OK) rc = scratch.ensure(threads, ads.max_cols, ads.max_nw);
+        if (rc == TGSF_OK) rc = scratch.ensure(ads.host, sms * 4, RES_THREADS);
         if (rc != TGSF_OK) { cleanup(); return rc; }
         cudaMemset(d_maps.p, 0, (size_t)2 * n_lib * sizeof(long long));
         long long *m5 = d_maps.as<long long>(), *m3 = m5 + n_lib;
         const AdapterCtx AC = ads.ctx();
         for (int a = 0; a < n_lib && n; ++a) {
-            rc = for_nw(ads.host[(size_t)a].nw, [&](auto nwc) {
+            const DevAdapter &Ah = ads.host[(size_t)a];
+            const int grid_a = Scratch::grid_for(sms * 4, RES_THREADS, 2 * Ah.qlen + 2, Ah.nw);
+            const u64 stride_a = (u64)grid_a * RES_THREADS;
+            rc = for_nw(Ah.nw, [&](auto nwc) {
                 constexpr int NW = decltype(nwc)::value;
-                k_lib_search<NW><<<sms * 4, RES_THREADS>>>(r5, n, row_len, AC, a, m5 + a, scratch.buf.as<u64>(), scratch.stride);
-                k_lib_search<NW><<<sms * 4, RES_THREADS>>>(r3, n, row_len, AC, a, m3 + a, scratch.buf.as<u64>(), scratch.stride);
+                k_lib_search<NW><<<grid_a, RES_THREADS>>>(r5, n, row_len, AC, a, m5 + a, scratch.buf.as<u64>(), stride_a);
+                k_lib_search<NW><<<grid_a, RES_THREADS>>>(r3, n, row_len, AC, a, m3 + a, scratch.buf.as<u64>(), stride_a);
                 return check_launch("k_lib_search");
             });
             if (rc != TGSF_OK) { cleanup(); return rc; }
@@ -1293,8 +1328,7 @@ int tgsf_align_hw(int device, const uint8_t *queries, const uint32_t *q_off, con
     if (rc == TGSF_OK) rc = d_toff.ensure(((size_t)n + 1) * sizeof(u32));
     if (rc == TGSF_OK) rc = d_k.ensure((size_t)n * sizeof(int));
     if (rc == TGSF_OK) rc = d_out.ensure((size_t)n * sizeof(tgsf_align_result));
-    const u64 threads = (u64)sms * 2 * RES_THREADS;
-    if (rc == TGSF_OK) rc = scratch.ensure(threads, ads.max_cols, ads.max_nw);
+    if (rc == TGSF_OK) rc = scratch.ensure(ads.host, sms * 2, RES_THREADS);
     if (rc != TGSF_OK) { cleanup(); return rc; }
     cudaError_t e = cudaSuccess;
     if (tbytes) e = cudaMemcpy(d_t.p, targets, tbytes, cudaMemcpyHostToDevice);
@@ -1303,14 +1337,17 @@ int tgsf_align_hw(int device, const uint8_t *queries, const uint32_t *q_off, con
     if (e == cudaSuccess) e = cudaMemset(d_out.p, 0, (size_t)n * sizeof(tgsf_align_result));
     if (e != cudaSuccess) { set_err("align upload: %s", cudaGetErrorString(e)); cleanup(); return TGSF_ERR_CUDA; }
     const AdapterCtx AC = ads.ctx();
-    for (int nw = 1; nw <= 4; ++nw) {
-        bool any = false;
-        for (u32 i = 0; i < n; ++i) any |= ads.host[i].nw == nw;
-        if (!any) continue;
+    for (int nw : {1, 2, 3, 4, 8, 16, 32}) {
+        int max_q = 0;
+        for (u32 i = 0; i < n; ++i)
+            if (ads.host[i].nw == nw) max_q = std::max(max_q, ads.host[i].qlen);
+        if (max_q == 0) continue;
+        const int grid_nw = Scratch::grid_for(sms * 2, RES_THREADS, 2 * max_q + 2, nw);
         rc = for_nw(nw, [&](auto nwc) {
             constexpr int NW = decltype(nwc)::value;
-            k_align_pairs<NW><<<sms * 2, RES_THREADS>>>(d_t.as<uint8_t>(), d_toff.as<u32>(), d_k.as<int>(), AC, n, NW,
-                                                        d_out.as<tgsf_align_result>(), scratch.buf.as<u64>(), scratch.stride);
+            k_align_pairs<NW><<<grid_nw, RES_THREADS>>>(d_t.as<uint8_t>(), d_toff.as<u32>(), d_k.as<int>(), AC, n, NW,
+                                                        d_out.as<tgsf_align_result>(), scratch.buf.as<u64>(),
+                                                        (u64)grid_nw * RES_THREADS);
             return check_launch("k_align_pairs");
         });
         if (rc != TGSF_OK) { cleanup(); return rc; }
