@@ -429,7 +429,54 @@ struct Selection {
     uint64_t downBases = 0, downNum = 0;
 };
 
-Selection select_reads(const RecIndex &idx, const Params &P) {
+// total_all: the reference's `totalSize` when it is known before the ranking (-F: get_fastx_SeqLen adds EVERY record,
+// also the earlier ones of a repeated name, T.cpp:2256-2269); 0 = sum over the ranked names (filter mode, T.cpp:2318-2322).
+// The ranking needs no sort: a histogram of the lengths gives the cut-off length and how many reads of exactly that
+// length are taken (the first ones in file order), in O(reads + longest read).
+Selection select_reads(const RecIndex &idx, const Params &P, uint64_t total_all = 0) {
+    Selection S;
+    const size_t n = idx.names.size();
+    S.keep.assign(n, 0);
+    int max_len = 0;
+    uint64_t totalSize = 0;
+    for (int l : idx.lens) { totalSize += (uint64_t)l; max_len = std::max(max_len, l); }
+    if (total_all) totalSize = total_all;
+    std::vector<uint32_t> hist((size_t)max_len + 2, 0);
+    for (int l : idx.lens) hist[(size_t)std::max(l, 0)]++;
+    // walk the lengths from the longest: reads are taken one by one until the target is met
+    uint64_t desired = 0;
+    bool by_bases = true;
+    if (P.GenomeSize > 0 && P.DesiredDepth > 0) desired = P.GenomeSize * (uint64_t)P.DesiredDepth;
+    else if (P.DesiredFrac > 0) desired = (uint64_t)(P.DesiredFrac * totalSize);
+    else if (P.DesiredNum > 0) { desired = (uint64_t)P.DesiredNum; by_bases = false; }
+    else return S;
+    int cut_len = -1;          // reads longer than this are all taken
+    uint64_t cut_take = 0;     // ... and this many of exactly this length
+    uint64_t added = 0;
+    for (int l = max_len; l >= 0 && cut_len < 0; --l) {
+        const uint64_t c = hist[(size_t)l];
+        if (!c) continue;
+        // the loop of get_reads_name takes a read, then tests `added >= desired`
+        const uint64_t unit = by_bases ? (uint64_t)l : 1;
+        uint64_t need;
+        if (added >= desired) need = 1;                              // (only possible before the first read: desired == 0)
+        else if (unit == 0) need = c + 1;                            // zero-length reads never reach the target
+        else need = (desired - added + unit - 1) / unit;             // reads of this length until added >= desired
+        if (need <= c) { cut_len = l; cut_take = need; }
+        else added += c * unit;
+    }
+    if (cut_len < 0) { cut_len = -1; cut_take = 0; }                 // target never met: everything is taken
+    uint64_t at_cut = 0;
+    for (size_t i = 0; i < n; i++) {
+        const int l = idx.lens[i];
+        bool k = l > cut_len;
+        if (l == cut_len && at_cut < cut_take) { k = true; ++at_cut; }
+        if (k) { S.keep[i] = 1; S.downBases += (uint64_t)l; S.downNum++; }
+    }
+    return S;
+}
+
+Selection select_reads_sorted(const RecIndex &idx, const Params &P, uint64_t total_all = 0) { // reference form (tests: TGSF_SELECT_SORT=1)
     Selection S;
     S.keep.assign(idx.names.size(), 0);
     std::vector<size_t> order(idx.names.size());
@@ -437,6 +484,7 @@ Selection select_reads(const RecIndex &idx, const Params &P) {
     std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return idx.lens[a] > idx.lens[b]; });
     uint64_t totalSize = 0;
     for (int l : idx.lens) totalSize += (uint64_t)l;
+    if (total_all) totalSize = total_all;
     auto take = [&](size_t i) { S.keep[i] = 1; S.downBases += (uint64_t)idx.lens[i]; S.downNum++; };
     if (P.GenomeSize > 0 && P.DesiredDepth > 0) {
         uint64_t added = 0, desired = P.GenomeSize * (uint64_t)P.DesiredDepth;
@@ -701,6 +749,15 @@ int main(int argc, char **argv) {
     report::Side rawSide, cleanSide;
     string tmpPath;
     RecIndex recIdx;
+    // Filter + downsample: the filtered records are kept in host memory for the second pass (sequence / quality bytes
+    // back to back + one entry per record); only past TGSF_DOWNSAMPLE_BUFFER_MB (default: a quarter of MemAvailable, at
+    // most 64 GB) they are spilled to the reference's uncompressed tmp file (T.cpp:3129-3137) and the run continues there.
+    struct MemRec { uint64_t off; uint32_t len; uint32_t name; };
+    std::vector<MemRec> mem_recs;
+    std::vector<string> mem_names;
+    string mem_seq, mem_qual;
+    bool mem_mode = false;
+    uint64_t mem_budget = 0;
     if (P.Filter || P.OnlyQC) {
     tlog("gpu prepass + resolve", T_ph.lap());
     // ---- contexts: one per GPU ---------------------------------------------------------------------
@@ -738,11 +795,25 @@ int main(int argc, char **argv) {
     tlog("tgsf_create", T_ph.lap());
     // ---- main pass -----------------------------------------------------------------------------------
     FILE *out = stdout;
-    if (P.Downsample) { // uncompressed tmp file like T.cpp:3129-3137
+    auto open_tmp = [&]() -> bool { // uncompressed tmp file like T.cpp:3129-3137
         string prefix = P.InFile;
         tmpPath = prefix + ".tmp." + std::to_string((long)getpid()) + (P.Outfq == 0 ? ".fa" : ".fq");
         out = fopen(tmpPath.c_str(), "wb");
-        if (!out) { cerr << "Error: Failed to open file: " << tmpPath << endl; return quit(1); }
+        if (!out) { cerr << "Error: Failed to open file: " << tmpPath << endl; return false; }
+        return true;
+    };
+    if (P.Downsample) {
+        uint64_t avail_mb = 0;
+        if (FILE *mi = fopen("/proc/meminfo", "r")) {
+            char line[256];
+            while (fgets(line, sizeof(line), mi)) { unsigned long long kb; if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) avail_mb = kb >> 10; }
+            fclose(mi);
+        }
+        uint64_t mb = std::min<uint64_t>(avail_mb / 4, 65536);
+        if (const char *e = getenv("TGSF_DOWNSAMPLE_BUFFER_MB")) mb = strtoull(e, nullptr, 10);
+        mem_budget = mb << 20;
+        mem_mode = mem_budget > 0;
+        if (!mem_mode && !open_tmp()) return quit(1);
     } else if (!P.OnlyQC && !P.OutFile.empty()) {
         out = fopen(P.OutFile.c_str(), "w+b"); // read-write: the plain writer maps the file
         if (!out) { cerr << "Error: Failed to open file: " << P.OutFile << endl; return quit(1); }
@@ -858,7 +929,33 @@ int main(int argc, char **argv) {
                     dst += '>'; dst += *nm[i]; dst += '\n'; dst.append(sq, e.len); dst += '\n';
                 }
             };
-            if (P.Downsample) {
+            if (P.Downsample && mem_mode) {
+                for (size_t i = 0; i < emits.size(); ++i) {
+                    const Emit &e = emits[i];
+                    const char *sq = (const char *)b.bases.data() + b.offsets[e.read] + e.start;
+                    mem_recs.push_back(MemRec{(uint64_t)mem_seq.size(), (uint32_t)e.len, (uint32_t)mem_names.size()});
+                    mem_names.push_back(*nm[i]);
+                    mem_seq.append(sq, e.len);
+                    if (P.Outfq == 1) mem_qual.append((const char *)b.quals.data() + b.offsets[e.read] + e.start, e.len);
+                    recIdx.add(*nm[i], (int)e.len);
+                }
+                if (mem_seq.size() + mem_qual.size() > mem_budget) { // over budget: spill what is buffered, continue on the file
+                    if (!open_tmp()) { cerr.flush(); fflush(nullptr); _exit(1); } // (writer thread: leave like quit())
+                    {
+                        string rec;
+                        for (const MemRec &r : mem_recs) {
+                            rec.clear();
+                            if (P.Outfq == 1) { rec += '@'; rec += mem_names[r.name]; rec += '\n'; rec.append(mem_seq, r.off, r.len); rec += "\n+\n"; rec.append(mem_qual, r.off, r.len); rec += '\n'; }
+                            else { rec += '>'; rec += mem_names[r.name]; rec += '\n'; rec.append(mem_seq, r.off, r.len); rec += '\n'; }
+                            fwrite(rec.data(), 1, rec.size(), out);
+                        }
+                    }
+                    mem_mode = false;
+                    mem_recs.clear(); mem_recs.shrink_to_fit();
+                    mem_names.clear(); mem_names.shrink_to_fit();
+                    string().swap(mem_seq); string().swap(mem_qual);
+                }
+            } else if (P.Downsample) {
                 for (size_t i = 0; i < emits.size(); ++i) {
                     format_rec(i, obuf);
                     recIdx.add(*nm[i], (int)emits[i].len);
@@ -1338,13 +1435,15 @@ int main(int argc, char **argv) {
         };
         Selection S;
         uint64_t downInNum = 0, downInBases = 0;
+        const bool from_memory = P.Filter && mem_mode; // the filtered records never left host memory
         const string downInput = P.Filter ? tmpPath : P.InFile;
         if (!P.Filter) { // get_fastx_SeqLen, T.cpp:2256-2269
             FastxReader rd(P.InFile);
             string name, seq, qual;
             while (rd.read(name, seq, qual)) { recIdx.add(name, (int)seq.size()); downInNum++; downInBases += seq.size(); }
         }
-        S = select_reads(recIdx, P);
+        S = getenv("TGSF_SELECT_SORT") ? select_reads_sorted(recIdx, P, P.Filter ? 0 : downInBases)
+                                       : select_reads(recIdx, P, P.Filter ? 0 : downInBases);
         // second pass (T.cpp:2346-2568): keep the selected names in file order and recompute the QC
         // tables of the kept reads on the GPU (a QC-only context: its "raw" tables are the report's
         // "after" column)
@@ -1354,7 +1453,7 @@ int main(int argc, char **argv) {
         tgsf_ctx *qctx = nullptr;
         if (tgsf_create(0, &qp, &qctx) != TGSF_OK) die_tgsf("tgsf_create (downsample QC)");
         Batch qb;
-        const bool dqual = file_type(downInput) == 1 || file_type(downInput) == 2;
+        const bool dqual = from_memory ? P.Outfq == 1 : (file_type(downInput) == 1 || file_type(downInput) == 2);
         auto flush = [&]() {
             if (!qb.n()) return;
             if (!qb.pack()) die_tgsf("tgsf_pack_bases");
@@ -1367,17 +1466,29 @@ int main(int argc, char **argv) {
         std::vector<int> downLens;
         uint64_t downBases = 0;
         {
-            FastxReader rd(downInput);
             string name, seq, qual, rec;
-            while (rd.read(name, seq, qual)) {
+            auto take = [&]() -> bool { // one candidate record in name / seq / qual
                 auto it = recIdx.pos.find(name);
-                if (it == recIdx.pos.end() || !S.keep[it->second]) continue;
+                if (it == recIdx.pos.end() || !S.keep[it->second]) return true;
                 rec.clear();
                 if (P.Outfq == 1) { rec += '@'; rec += name; rec += '\n'; rec += seq; rec += "\n+\n"; rec += qual; rec += '\n'; }
                 else { rec += '>'; rec += name; rec += '\n'; rec += seq; rec += '\n'; }
                 emit(rec.data(), rec.size());
-                if (!qb.add(name, seq, qual, dqual)) { cerr << "Error: out of pinned host memory" << endl; return quit(1); }
+                if (!qb.add(name, seq, qual, dqual)) { cerr << "Error: out of pinned host memory" << endl; return false; }
                 if (qb.used >= P.batch_bases) flush();
+                return true;
+            };
+            if (from_memory) {
+                for (const MemRec &r : mem_recs) {
+                    name = mem_names[r.name];
+                    seq.assign(mem_seq, r.off, r.len);
+                    if (dqual) qual.assign(mem_qual, r.off, r.len);
+                    if (!take()) return quit(1);
+                }
+            } else {
+                FastxReader rd(downInput);
+                while (rd.read(name, seq, qual))
+                    if (!take()) return quit(1);
             }
             flush();
         }

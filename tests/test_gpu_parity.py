@@ -982,3 +982,55 @@ def test_host_cli_long_adapter_file_vs_reference_cli(tmp_path):
     assert (h_rc, r_rc) == (0, 0), h_err
     assert h_out == r_out and len(h_out) > 0
     assert _info(h_err) == _info(r_err)
+
+
+@pytest.mark.parametrize("args", [
+    ["-x", "hifi", "-g", "100k", "-d", "8", "-k", "11", "-p", "40", "-5", "0", "-3", "0"],
+    ["-x", "hifi", "-R", "0.3", "-5", "3", "-3", "2"],
+    ["-x", "hifi", "-r", "41"],
+    ["-F", "-R", "0.4"],
+])
+def test_host_cli_downsampling_in_memory_spill_and_selection_forms(args, monkeypatch, tmp_path):
+    """Filter + downsample keeps the filtered records in host memory: no `<input>.tmp.<pid>` file appears next to
+    the input while the run is going (the reference writes one, T.cpp:3129-3137).  Forcing the spill to the tmp file
+    (buffer of 0 MB / of 1 MB, exceeded after the first batches) and the sort-based selection (the reference's form)
+    must give the same records and INFO lines as the default (in memory, histogram cut-off)."""
+    import os
+    import subprocess
+    import threading
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "src", "tgsfilter")
+    batch = synth.make_config(5, 700, max_len=30000)  # ordinary lengths: many ties, also at the cut-off
+    fq = tmp_path / "in.fq"
+    fq.write_bytes(batch.to_fastq())
+    monkeypatch.setenv("TGSF_BATCH_MB", "2")
+
+    def run(env_extra, out_name):
+        env = dict(os.environ)
+        env.update(env_extra)
+        seen = []
+        stop = threading.Event()
+
+        def watch():
+            while not stop.is_set():
+                seen.extend(f for f in os.listdir(tmp_path) if ".tmp." in f)
+                time.sleep(0.002)
+        th = threading.Thread(target=watch)
+        th.start()
+        pr = subprocess.run([exe, "-i", str(fq), "-o", str(tmp_path / out_name)] + args, stdout=subprocess.PIPE,
+                            stderr=subprocess.PIPE, env=env, timeout=600)
+        stop.set()
+        th.join()
+        assert pr.returncode == 0, pr.stderr.decode()[-800:]
+        assert not [f for f in os.listdir(tmp_path) if ".tmp." in f]  # removed at the end in every mode
+        return (tmp_path / out_name).read_bytes(), _info(pr.stderr.decode()), bool(seen)
+
+    out0, info0, tmp0 = run({}, "a.fq")
+    out1, info1, tmp1 = run({"TGSF_DOWNSAMPLE_BUFFER_MB": "0"}, "b.fq")
+    out2, info2, _ = run({"TGSF_DOWNSAMPLE_BUFFER_MB": "1"}, "c.fq")
+    out3, info3, _ = run({"TGSF_SELECT_SORT": "1"}, "d.fq")
+    assert len(out0) > 0 and out1 == out0 and out2 == out0 and out3 == out0
+    assert info1 == info0 and info2 == info0 and info3 == info0
+    if "-F" not in args:
+        assert not tmp0, "the default run wrote a tmp file"
