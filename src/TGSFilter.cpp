@@ -557,7 +557,18 @@ int main(int argc, char **argv) {
     std::deque<std::unique_ptr<ingest::RawBatch>> pending;
     bool input_done = false;
     uint64_t pending_bytes = 0;
-    const uint64_t prepass_budget = (uint64_t)((getenv("TGSF_PREPASS_BUFFER_MB") ? atof(getenv("TGSF_PREPASS_BUFFER_MB")) : 24576.0) * 1048576.0);
+    // pre-pass: parsed batches are held (pageable host memory) until the sample is complete; past this budget the main pass
+    // re-reads the input instead (two-pass mode, like the reference).  Default: a quarter of MemAvailable, at most 24 GB.
+    double prepass_mb = 24576.0;
+    if (FILE *mi = fopen("/proc/meminfo", "r")) {
+        char line[256];
+        unsigned long long kb;
+        while (fgets(line, sizeof(line), mi))
+            if (sscanf(line, "MemAvailable: %llu kB", &kb) == 1) prepass_mb = std::min(prepass_mb, (double)(kb >> 10) / 4.0);
+        fclose(mi);
+    }
+    if (getenv("TGSF_PREPASS_BUFFER_MB")) prepass_mb = atof(getenv("TGSF_PREPASS_BUFFER_MB"));
+    const uint64_t prepass_budget = (uint64_t)(prepass_mb * 1048576.0);
     std::thread reader;
     std::unique_ptr<ingest::ParallelReader> preader; // plain files: parallel chunk parser
     auto next_parsed = [&]() { return preader ? preader->pop() : parsed.pop(); };

@@ -659,6 +659,8 @@ private:
             if (bs < 26 || b + bs > size_) break; // not a (complete) BGZF block: the remainder is streamed
             uint32_t isize;
             memcpy(&isize, base_ + b + bs - 4, 4);
+            if (isize > 65536u) break; // the BGZF limit per block (SAM spec 4.1): a larger claim is corrupt, the remainder is
+                                       // streamed by the checked sequential reader instead of sizing a buffer from it
             out += isize;
             b += bs;
         }

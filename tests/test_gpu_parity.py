@@ -1034,3 +1034,37 @@ def test_host_cli_downsampling_in_memory_spill_and_selection_forms(args, monkeyp
     assert info1 == info0 and info2 == info0 and info3 == info0
     if "-F" not in args:
         assert not tmp0, "the default run wrote a tmp file"
+
+
+def test_counter_block_grows_with_the_longest_read():
+    """A context created for short reads (max_read_len 3 000) meets longer and longer reads batch after batch: the
+    per-100 bp tables move to a larger layout before the batch is launched (the reference sizes them per read,
+    T.cpp:1445), nothing accumulated so far is lost, and a read beyond the old limit is no longer an error."""
+    from tgsfilter_b200.engine import Counters
+    full = synth.make_config(2, 240, max_len=60000)
+    lens = np.diff(full.offsets.astype(np.int64))
+    order = np.argsort(lens, kind="stable")  # ascending: every batch brings longer reads than the one before
+    seqs = [full.read(int(i))[0].tobytes() for i in order]
+    quals = [full.read(int(i))[1].tobytes() for i in order]
+    batches = [synth.pack_reads(seqs[a:a + 60], quals[a:a + 60]) for a in range(0, 240, 60)]
+    params = synth.config_params(2)
+    params.max_read_len = 3000
+    with FilterEngine(params) as eng:
+        for b in batches:
+            eng.run(b)
+        g = eng.counters()
+    assert g.layout.max_bins > 3000 // 100 + 1
+    big = synth.config_params(2)
+    big.max_read_len = 100000
+    o_cnt = None
+    for b in batches:
+        _, _, o_cnt = oracle_lib.run(big, b, o_cnt)
+    o = Counters(o_cnt, oracle_lib.layout(big))
+    assert np.array_equal(g.drop_info, o.drop_info)
+    assert np.array_equal(g.raw_hist, o.raw_hist) and np.array_equal(g.clean_hist, o.clean_hist)
+    for name in Counters.TABLES_BC:
+        assert np.array_equal(getattr(g, name), getattr(o, name)), name
+    for name in Counters.TABLES_BIN:
+        a, b = getattr(g, name), getattr(o, name)
+        m = min(len(a), len(b))
+        assert np.array_equal(a[:m], b[:m]) and not a[m:].any() and not b[m:].any(), name

@@ -869,6 +869,37 @@ int tgsf_host_free(void *ptr) {
     return TGSF_OK;
 }
 
+// The per-100 bp tables are sized by the longest read the context has seen so far (the reference sizes them by
+// every read's own length, T.cpp:1445): a batch with a longer read first moves the counter block to a larger layout.
+// Only the four bin tables at the end of the block depend on the length; everything in front keeps its offset.
+static int grow_counters_to(tgsf_ctx *c, u32 new_bins) { // exactly new_bins bins per table
+    if (new_bins <= c->P.L.max_bins) return TGSF_OK;
+    for (auto &s : c->slots) // batches in flight were launched on the old block
+        if (s.busy) CU(cudaStreamSynchronize(s.stream));
+    const tgsf_counter_layout OL = c->P.L;
+    tgsf_counter_layout NL;
+    tgsf_make_layout(OL.bc_len, (int32_t)((u64)(new_bins - 1) * SCAN_BIN), &NL);
+    DBuf nb;
+    TRY(nb.ensure((size_t)NL.n_u64 * sizeof(u64)));
+    CU(cudaMemset(nb.p, 0, (size_t)NL.n_u64 * sizeof(u64)));
+    const u64 *o = c->counters.as<u64>();
+    u64 *n = nb.as<u64>();
+    CU(cudaMemcpy(n, o, (size_t)OL.raw_bin_cnt * sizeof(u64), cudaMemcpyDeviceToDevice));
+    const u32 osec[4] = {OL.raw_bin_cnt, OL.raw_bin_qual, OL.clean_bin_cnt, OL.clean_bin_qual};
+    const u32 nsec[4] = {NL.raw_bin_cnt, NL.raw_bin_qual, NL.clean_bin_cnt, NL.clean_bin_qual};
+    for (int i = 0; i < 4; ++i)
+        CU(cudaMemcpy(n + nsec[i], o + osec[i], (size_t)OL.max_bins * 5 * sizeof(u64), cudaMemcpyDeviceToDevice));
+    c->counters.release();
+    c->counters = nb;
+    c->P.L = NL;
+    return TGSF_OK;
+}
+static int grow_counters(tgsf_ctx *c, u64 longest) { // room for a read of `longest` bases (+ 25 % slack when growing)
+    if (longest / SCAN_BIN + 1 <= (u64)c->P.L.max_bins) return TGSF_OK;
+    if (longest > 0x7fffffffull) { set_err("a read of %llu bases is longer than 2^31 - 1", (unsigned long long)longest); return TGSF_ERR_INVALID; }
+    return grow_counters_to(c, (u32)(std::min<u64>(longest + longest / 4 + 1024, 0x7fffffffull) / SCAN_BIN + 1));
+}
+
 struct PackedIn { // optional 2-bit input of tgsf_submit_packed
     const uint8_t *packed = nullptr;
     const u64 *exc_pos = nullptr;
@@ -883,6 +914,11 @@ static int submit_common(tgsf_ctx *c, const uint8_t *bases, const uint8_t *quals
     if (n_reads > (1u << 24)) { set_err("more than 2^24 reads in one batch"); return TGSF_ERR_INVALID; }
     if (c->outstanding == c->slots.size()) { set_err("all %zu slots busy: collect first", c->slots.size()); return TGSF_ERR_STATE; }
     CU(cudaSetDevice(c->device));
+    if (!on_device && n_reads) { // host offsets: make room for the longest read of this batch before anything is launched
+        u64 longest = 0;
+        for (u32 i = 0; i < n_reads; ++i) longest = std::max<u64>(longest, offsets[i + 1] - offsets[i]);
+        TRY(grow_counters(c, longest));
+    }
     Slot &s = c->slots[c->head];
     s.has_qual = quals != nullptr;
     s.n_bases = n_bases;
@@ -1186,8 +1222,15 @@ int tgsf_allreduce(tgsf_ctx **ctxs, int n) {
     for (int i = 0; i < n; ++i) {
         if (!ctxs[i]) { set_err("allreduce: NULL context"); return TGSF_ERR_INVALID; }
         if (ctxs[i]->outstanding) { set_err("allreduce: collect all batches first"); return TGSF_ERR_STATE; }
-        if (ctxs[i]->P.L.n_u64 != ctxs[0]->P.L.n_u64) { set_err("allreduce: counter layouts differ"); return TGSF_ERR_INVALID; }
+        if (ctxs[i]->P.L.bc_len != ctxs[0]->P.L.bc_len) { set_err("allreduce: counter layouts differ"); return TGSF_ERR_INVALID; }
     }
+    u32 bins = 0; // contexts that met longer reads have grown their bin tables: bring all to the largest layout
+    for (int i = 0; i < n; ++i) bins = std::max(bins, ctxs[i]->P.L.max_bins);
+    for (int i = 0; i < n; ++i)
+        if (ctxs[i]->P.L.max_bins < bins) {
+            CU(cudaSetDevice(ctxs[i]->device));
+            TRY(grow_counters_to(ctxs[i], bins));
+        }
     if (n == 1) return TGSF_OK;
     tgsf_ctx *root = ctxs[0];
     const u32 words = root->P.L.n_u64;

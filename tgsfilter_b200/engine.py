@@ -203,6 +203,8 @@ class FilterEngine:
 
     # -- counters -------------------------------------------------------------------------------
     def counters(self) -> Counters:
+        # the block grows when a batch brings a read longer than every one before it: ask again
+        _capi.check(self._lib.tgsf_counter_layout_get(self._ctx, C.byref(self.layout)), "tgsf_counter_layout_get")
         flat = np.zeros(self.layout.n_u64, dtype=np.uint64)
         _capi.check(self._lib.tgsf_counters(self._ctx, flat.ctypes.data, flat.size), "tgsf_counters")
         return Counters(flat, self.layout)
