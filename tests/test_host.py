@@ -53,7 +53,7 @@ def test_no_cpu_fallback_engine_fails_loudly_without_gpu():
 def test_create_rejects_bad_parameters_before_touching_the_gpu():
     lib = _capi.load()
     ctx = C.c_void_p()
-    p = FilterParams(adapters=[b"A" * 300]).apply_read_type("ont")
+    p = FilterParams(adapters=[b"A" * 2049]).apply_read_type("ont")  # TGSF_MAX_ADAPTER_LEN is 2048
     cp, keep = p.to_c()
     assert lib.tgsf_create(0, C.byref(cp), C.byref(ctx)) == _capi.TGSF_ERR_INVALID
     assert b"adapter" in lib.tgsf_last_error()
