@@ -85,6 +85,7 @@ def static_config(cfg: int, n_reads: int, strong: bool) -> dict:
     """The `config` object: a pure function of the command line, identical in both arms."""
     return {"workload": workload_name(cfg, n_reads, strong), "cli": " ".join(CONFIG_CLI[cfg]),
             "reads": n_reads, "reads_are": "total over all GPUs" if strong else "per GPU",
+            "batches": "16, dealt round-robin" if strong else "ceil(reads / 400000), at least --split; two in flight",
             "seed": SEED0 + cfg,
             "l2": "inputs (2 B/base, >= 0.5 GB per launch) are larger than the 126 MB L2"}
 
@@ -446,8 +447,9 @@ def main():
     ap.add_argument("--strong", action="store_true", default=os.environ.get("TGSF_BENCH_STRONG", "") not in ("", "0"),
                     help="strong scaling: one dataset dealt to the ranks, counter allreduce inside the step; env TGSF_BENCH_STRONG=1")
     ap.add_argument("--reads", type=int, default=0, help="reads in the dataset (0 = the config's full size)")
-    ap.add_argument("--split", type=int, default=int(os.environ.get("TGSF_BENCH_SPLIT", "0")),
-                    help="weak mode: feed the dataset as at least this many batches (two are in flight at a time)")
+    ap.add_argument("--split", type=int, default=int(os.environ.get("TGSF_BENCH_SPLIT", "-1")),
+                    help="weak mode: feed the dataset as at least this many batches (two are in flight at a time, so the "
+                         "HBM-bound scans of one overlap the ALU-bound adapter scan of the other); default 2 for configs 2 and 3")
     ap.add_argument("--sample-reads", type=int, default=0, help="CPU reference: cap the reads per step (0 = whole dataset / time budget)")
     ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -456,6 +458,8 @@ def main():
     args.warmup = max(args.warmup, 0)
     if args.config not in CONFIG_READS:
         raise SystemExit(f"--config must be one of {sorted(CONFIG_READS)}")
+    if args.split < 0:
+        args.split = 2 if args.config in (2, 3) else 0
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)

@@ -370,81 +370,106 @@ k_mid_emit(DevBatch B, AdapterCtx C, int a, int end_len, int chunk_shift, int ex
 // out: end_n [n_reads][n_adapters][2] location counts (0 if the thresholds fail),
 //      end_pos[n_reads][n_adapters][2]: side 0 -> max te (region {0, te}), side 1 -> min ts.
 // ---------------------------------------------------------------------------------------------
-template <int NW>
+// AP adapters (same word count) per thread: the forward scan of phase 1 is one serial chain per adapter, so two
+// chains fed by the same byte loads double the instruction-level parallelism (as in k_mid_scan).
+template <int NW, int AP>
 __global__ void __launch_bounds__(RES_THREADS)
-k_ends(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
+k_ends(DevBatch B, AdapterCtx C, int a0, int a1, int end_len, int n_adapters,
        const int *__restrict__ read_active, int *__restrict__ end_n, int *__restrict__ end_pos,
        u64 *scratch, u64 scratch_stride) {
-    extern __shared__ u64 s_tab_smem[]; // hw | fw | rv | rvhw tables of adapter a (NW <= 4; longer adapters: global memory)
-    const DevAdapter A = C.ad[a];
-    const u64 *s_tab = s_tab_smem;
-    if (NW > 4) {
-        s_tab = C.peq_pool + A.peq_off;
-    } else {
-        const u64 *src = C.peq_pool + A.peq_off;
-        for (int i = threadIdx.x; i < 4 * 256 * NW; i += RES_THREADS) s_tab_smem[i] = src[i];
-        __syncthreads();
+    extern __shared__ u64 s_tab_smem[]; // per adapter: hw | fw | rv | rvhw tables (NW <= 4; longer adapters: global memory)
+    const int aidx[2] = {a0, a1};
+    DevAdapter A[AP];
+    AdapterTables T[AP];
+    const u64 *rvhw[AP];
+#pragma unroll
+    for (int x = 0; x < AP; ++x) {
+        A[x] = C.ad[aidx[x]];
+        const u64 *tab = C.peq_pool + A[x].peq_off;
+        if (NW <= 4) {
+            u64 *dst = s_tab_smem + (size_t)x * 4 * 256 * NW;
+            for (int i = threadIdx.x; i < 4 * 256 * NW; i += RES_THREADS) dst[i] = tab[i];
+            tab = dst;
+        }
+        T[x].hw = tab;
+        T[x].fw = tab + 256 * NW;
+        T[x].rv = tab + 512 * NW;
+        T[x].qlen = A[x].qlen;
+        rvhw[x] = tab + 768 * NW;
     }
-    AdapterTables T;
-    T.hw = s_tab;
-    T.fw = s_tab + 256 * NW;
-    T.rv = s_tab + 512 * NW;
-    T.qlen = A.qlen;
-    const u64 *rvhw = s_tab + 768 * NW;
+    if (NW <= 4) __syncthreads();
     const u64 tid = (u64)blockIdx.x * RES_THREADS + threadIdx.x;
     const u64 total = (u64)B.n_reads * 2;
     for (u64 w = tid; w < total; w += (u64)gridDim.x * RES_THREADS) {
         const int side = w >= B.n_reads ? 1 : 0;
         const u32 r = (u32)(side ? w - B.n_reads : w);
-        const u64 oidx = ((u64)r * n_adapters + a) * 2 + side;
-        int n_loc = 0, pos = 0;
-        if (read_active[r] && A.k_end > 0) {
-            const u64 rs = B.offsets[r];
-            const int tLen = (int)(B.offsets[r + 1] - rs);
-            int checkLen = end_len + A.end_extra; // T.cpp:1267
+        const bool active = read_active[r] != 0;
+        const u64 rs = B.offsets[r];
+        const int tLen = (int)(B.offsets[r + 1] - rs);
+        u64 lo[AP], hi[AP];
+        Myers<NW> s[AP];
+        int d[AP], cnt[AP];
+        u64 first[AP], last[AP];
+        u64 lo_min = ~0ull, hi_max = 0;
+#pragma unroll
+        for (int x = 0; x < AP; ++x) {
+            int checkLen = end_len + A[x].end_extra; // T.cpp:1267
             if (checkLen > tLen) checkLen = tLen;
-            if (checkLen >= 5) {
-                const u64 lo = side == 0 ? rs : rs + (u64)(tLen - checkLen);
-                const u64 hi = lo + (u64)checkLen;
-                // phase 1
-                Myers<NW> s;
-                myers_init_hw<NW>(s, T.qlen);
-                int d = 0x7fffffff, cnt = 0;
-                u64 first = 0, last = 0;
+            const bool on = active && A[x].k_end > 0 && checkLen >= 5;
+            lo[x] = side == 0 ? rs : rs + (u64)(tLen - checkLen);
+            hi[x] = on ? lo[x] + (u64)checkLen : lo[x]; // empty window: nothing to scan
+            if (on) { lo_min = min(lo_min, lo[x]); hi_max = max(hi_max, hi[x]); }
+            myers_init_hw<NW>(s[x], T[x].qlen);
+            d[x] = 0x7fffffff;
+            cnt[x] = 0;
+            first[x] = last[x] = 0;
+        }
+        // phase 1 (all adapters of the thread off the same byte)
 #pragma unroll 4
-                for (u64 p = lo; p < hi; ++p) {
-                    myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(B.bases + p) * NW, 0);
-                    if (s.score < d) { d = s.score; cnt = 1; first = p; last = p; }
-                    else if (s.score == d) { ++cnt; last = p; }
-                }
-                if (d <= A.k_end) {
-                    // phase 2
-                    const u64 s0 = shw_start<NW>(T, B.bases, lo, first, d);
-                    int ok = mlen_decision(T.qlen, (int)(first - s0 + 1), d, A.thr_end);
-                    if (ok < 0) {
-                        const int alen = nw_traceback_len<NW>(T, B.bases, s0, first, scratch + tid, scratch_stride);
-                        ok = (alen - d >= A.thr_end) ? 1 : 0;
-                    }
-                    if (ok) {
-                        n_loc = cnt;
-                        if (side == 0) {
-                            pos = (int)(last - rs) + 1; // te of the last location, T.cpp:1286
-                        } else {
-                            // phase 3
-                            myers_init_hw<NW>(s, T.qlen);
-                            u64 leftmost = s0;
-#pragma unroll 4
-                            for (u64 p = hi; p-- > lo;) {
-                                myers_step<NW, 0, true>(s, rvhw + (u32)__ldg(B.bases + p) * NW, 0);
-                                if (s.score == d) leftmost = p;
-                            }
-                            pos = (int)(leftmost - rs); // min ts, T.cpp:1310
-                        }
-                    }
+        for (u64 p = lo_min; p < hi_max; ++p) {
+            const u32 byte = (u32)__ldg(B.bases + p);
+#pragma unroll
+            for (int x = 0; x < AP; ++x) {
+                if (AP == 1 || (p >= lo[x] && p < hi[x])) {
+                    myers_step<NW, 0, true>(s[x], T[x].hw + byte * NW, 0);
+                    if (s[x].score < d[x]) { d[x] = s[x].score; cnt[x] = 1; first[x] = p; last[x] = p; }
+                    else if (s[x].score == d[x]) { ++cnt[x]; last[x] = p; }
                 }
             }
         }
-        end_n[oidx] = n_loc;
-        end_pos[oidx] = pos;
+#pragma unroll
+        for (int x = 0; x < AP; ++x) {
+            if (AP == 2 && x == 1 && a1 == a0) break; // odd adapter out: the second lane of the pair is a copy
+            const u64 oidx = ((u64)r * n_adapters + aidx[x]) * 2 + side;
+            int n_loc = 0, pos = 0;
+            if (hi[x] > lo[x] && d[x] <= A[x].k_end) {
+                // phase 2
+                const u64 s0 = shw_start<NW>(T[x], B.bases, lo[x], first[x], d[x]);
+                int ok = mlen_decision(T[x].qlen, (int)(first[x] - s0 + 1), d[x], A[x].thr_end);
+                if (ok < 0) {
+                    const int alen = nw_traceback_len<NW>(T[x], B.bases, s0, first[x], scratch + tid, scratch_stride);
+                    ok = (alen - d[x] >= A[x].thr_end) ? 1 : 0;
+                }
+                if (ok) {
+                    n_loc = cnt[x];
+                    if (side == 0) {
+                        pos = (int)(last[x] - rs) + 1; // te of the last location, T.cpp:1286
+                    } else {
+                        // phase 3
+                        Myers<NW> sr;
+                        myers_init_hw<NW>(sr, T[x].qlen);
+                        u64 leftmost = s0;
+#pragma unroll 4
+                        for (u64 p = hi[x]; p-- > lo[x];) {
+                            myers_step<NW, 0, true>(sr, rvhw[x] + (u32)__ldg(B.bases + p) * NW, 0);
+                            if (sr.score == d[x]) leftmost = p;
+                        }
+                        pos = (int)(leftmost - rs); // min ts, T.cpp:1310
+                    }
+                }
+            }
+            end_n[oidx] = n_loc;
+            end_pos[oidx] = pos;
+        }
     }
 }

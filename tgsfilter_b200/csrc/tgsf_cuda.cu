@@ -244,6 +244,7 @@ struct tgsf_ctx {
     bool kmer_force_bitmap = false; // TGSF_KMER_BITMAP=1: shared-memory bitmap passes also for single-tile pieces
     bool kmer_force_tag32 = false;  // TGSF_KMER_TAG32=1: k <= 12 stays on k_kmer_smem alone (round-1 kernel; A/B, tests)
     int kmer16_ctas_per_sm = 2;
+    int mid_ctas_per_sm = 0; // TGSF_MID_CTAS=n: cap on resident k_mid_scan CTAs per SM (0 = as many as fit)
     u32 kmer16_list_cap = KMER16_LIST_CAP; // TGSF_KMER16_LIST_CAP=n: smaller pending list (tests of the retry path)
     float last_kernel_ms = 0, last_total_ms = 0;
     float last_stage_ms[TGSF_N_STAGES] = {};
@@ -516,6 +517,7 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                     auto launch = [&](auto kern, size_t smem) {
                         int occ = 0; // persistent grid: exactly the resident CTA count
                         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MID_THREADS, smem) != cudaSuccess || occ < 1) occ = 4;
+                        if (c->mid_ctas_per_sm > 0) occ = std::min(occ, c->mid_ctas_per_sm);
                         kern<<<c->sm_count * occ, MID_THREADS, smem, st>>>(
                             s.B, AC, M, s.chunks.as<ChunkEntry>(), s.chunk_perm.as<u32>(), n_chunks_ptr,
                             s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
@@ -536,23 +538,49 @@ int launch_head(tgsf_ctx *c, Slot &s) {
         CU(cudaEventRecord(s.ev_stage[3], st));
         for (int a = 0; a < A; ++a) {
             const DevAdapter &Ah = c->ads.host[(size_t)a];
+            if (Ah.k_mid <= 0) continue;
             const int grid_a = Scratch::grid_for(res_grid, RES_THREADS, 2 * Ah.qlen + 2, Ah.nw);
-            const u64 stride_a = (u64)grid_a * RES_THREADS;
             TRY(for_nw(Ah.nw, [&](auto nwc) {
                 constexpr int NW = decltype(nwc)::value;
-                if (Ah.k_mid > 0) {
-                    k_mid_count<NW><<<grid_a, RES_THREADS, 0, st>>>(
-                        s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(), s.chunks_cap,
-                        s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
-                        s.mid_n.as<u32>(), s.scratch.buf.as<u64>(), stride_a);
-                    c->launches++;
-                }
-                k_ends<NW><<<grid_a, RES_THREADS, NW <= 4 ? 4 * 256 * NW * sizeof(u64) : 0, st>>>(s.B, AC, a, P.end_len, A, s.read_active.as<int>(),
-                                                            s.end_n.as<int>(), s.end_pos.as<int>(),
-                                                            s.scratch.buf.as<u64>(), stride_a);
+                k_mid_count<NW><<<grid_a, RES_THREADS, 0, st>>>(
+                    s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(), s.chunks_cap,
+                    s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
+                    s.mid_n.as<u32>(), s.scratch.buf.as<u64>(), (u64)grid_a * RES_THREADS);
                 c->launches++;
-                return check_launch("k3 resolve");
+                return check_launch("k_mid_count");
             }));
+        }
+        // end windows: adapters of one or two words go two per thread (paired by word count)
+        for (int nw : {1, 2, 3, 4, 8, 16, 32}) {
+            std::vector<int> grp;
+            for (int a = 0; a < A; ++a)
+                if (c->ads.host[(size_t)a].nw == nw) grp.push_back(a);
+            const size_t step = nw <= 2 ? 2 : 1;
+            for (size_t i = 0; i < grp.size(); i += step) {
+                const int a0 = grp[i], a1 = (step == 2 && i + 1 < grp.size()) ? grp[i + 1] : grp[i];
+                const int qmax = std::max(c->ads.host[(size_t)a0].qlen, c->ads.host[(size_t)a1].qlen);
+                const int grid_a = Scratch::grid_for(res_grid, RES_THREADS, 2 * qmax + 2, nw);
+                const u64 stride_a = (u64)grid_a * RES_THREADS;
+                TRY(for_nw(nw, [&](auto nwc) {
+                    constexpr int NW = decltype(nwc)::value;
+                    if constexpr (NW <= 2) {
+                        if (a1 != a0)
+                            k_ends<NW, 2><<<grid_a, RES_THREADS, 2 * 4 * 256 * NW * sizeof(u64), st>>>(
+                                s.B, AC, a0, a1, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
+                                s.scratch.buf.as<u64>(), stride_a);
+                        else
+                            k_ends<NW, 1><<<grid_a, RES_THREADS, 4 * 256 * NW * sizeof(u64), st>>>(
+                                s.B, AC, a0, a0, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
+                                s.scratch.buf.as<u64>(), stride_a);
+                    } else {
+                        k_ends<NW, 1><<<grid_a, RES_THREADS, NW <= 4 ? 4 * 256 * NW * sizeof(u64) : 0, st>>>(
+                            s.B, AC, a0, a0, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
+                            s.scratch.buf.as<u64>(), stride_a);
+                    }
+                    c->launches++;
+                    return check_launch("k_ends");
+                }));
+            }
         }
         TRY(exclusive_scan(c, st, s.mid_n.as<u32>(), s.mid_off.as<u32>(), n * (u32)A, s.scan_tmp.as<u32>(),
                            s.scan_tmp.cap / sizeof(u32)));
@@ -817,6 +845,7 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
         c->kmer_force_l2 = getenv("TGSF_KMER_L2") != nullptr;
         c->kmer_force_bitmap = getenv("TGSF_KMER_BITMAP") != nullptr;
         c->kmer_force_tag32 = getenv("TGSF_KMER_TAG32") != nullptr;
+        if (const char *e = getenv("TGSF_MID_CTAS")) c->mid_ctas_per_sm = atoi(e);
         if (const char *e = getenv("TGSF_KMER16_LIST_CAP")) c->kmer16_list_cap = (u32)std::min<long>(std::max<long>(atol(e), 32), (long)KMER16_LIST_CAP);
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
