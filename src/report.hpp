@@ -299,15 +299,40 @@ inline void write_html(const std::string &path, const std::string &qcType, const
         }
     }
     o << "}\n" << "</script>\n";
-    // this repo's own minimal viewer: one line/bar chart per key when the chart library is reachable
-    o << "<script src=\"https://cdn.jsdelivr.net/npm/echarts@5/dist/echarts.min.js\"></script>\n<script>\n"
-         "if (window.echarts) for (const k in data) { const d = data[k]; const el = document.createElement('div');\n"
-         "  el.className = 'plot'; document.getElementById('plots').appendChild(el);\n"
-         "  const multi = d.y.length && typeof d.y[0] === 'object';\n"
-         "  echarts.init(el).setOption({title: {text: k}, tooltip: {trigger: 'axis'}, legend: {top: 24},\n"
-         "    xAxis: {type: 'category', data: d.x}, yAxis: {type: 'value'},\n"
-         "    series: multi ? d.y.map(s => ({name: s.name, type: 'line', showSymbol: false, data: s.data}))\n"
-         "                  : [{type: k.endsWith('LenDis') ? 'bar' : 'line', showSymbol: false, data: d.y}]}); }\n"
+    // this repo's own minimal viewer: one canvas per key, drawn by the few lines below (no external library, the
+    // report works offline like the reference's, which embeds a 1 MB copy of echarts instead)
+    o << "<script>\n"
+         "(function () {\n"
+         "  var colors = ['#1f77b4', '#d62728', '#2ca02c', '#ff7f0e', '#9467bd', '#8c564b'];\n"
+         "  function draw(key, d) {\n"
+         "    var box = document.createElement('div'); box.className = 'plot';\n"
+         "    var cv = document.createElement('canvas'); cv.width = 720; cv.height = 360; box.appendChild(cv);\n"
+         "    document.getElementById('plots').appendChild(box);\n"
+         "    var g = cv.getContext('2d'), L = 56, R = 12, T = 30, B = 34, W = cv.width - L - R, H = cv.height - T - B;\n"
+         "    var multi = d.y.length && typeof d.y[0] === 'object';\n"
+         "    var series = multi ? d.y : [{name: '', data: d.y}];\n"
+         "    var n = d.x.length, ymax = 0;\n"
+         "    series.forEach(function (s) { s.data.forEach(function (v) { if (v > ymax) ymax = v; }); });\n"
+         "    if (ymax <= 0) ymax = 1;\n"
+         "    g.font = '13px sans-serif'; g.fillStyle = '#000'; g.fillText(key, L, 18);\n"
+         "    g.strokeStyle = '#999'; g.strokeRect(L, T, W, H); g.font = '11px sans-serif';\n"
+         "    for (var t = 0; t <= 4; t++) { var yy = T + H - H * t / 4; g.fillText((ymax * t / 4).toPrecision(3), 4, yy + 4);\n"
+         "      g.beginPath(); g.moveTo(L, yy); g.lineTo(L + W, yy); g.strokeStyle = '#eee'; g.stroke(); }\n"
+         "    for (var t = 0; t <= 6 && n > 0; t++) { var i = Math.min(n - 1, Math.round((n - 1) * t / 6));\n"
+         "      g.fillStyle = '#000'; g.fillText(String(d.x[i]), L + (n > 1 ? W * i / (n - 1) : 0) - 8, T + H + 16); }\n"
+         "    var bar = /LenDis$/.test(key);\n"
+         "    series.forEach(function (s, k) {\n"
+         "      g.strokeStyle = g.fillStyle = colors[k % colors.length];\n"
+         "      if (bar) { var bw = Math.max(1, W / Math.max(n, 1) - 1);\n"
+         "        s.data.forEach(function (v, i) { var h = H * v / ymax; g.fillRect(L + W * i / Math.max(n, 1), T + H - h, bw, h); });\n"
+         "      } else { g.beginPath();\n"
+         "        s.data.forEach(function (v, i) { var x = L + (n > 1 ? W * i / (n - 1) : 0), y = T + H - H * v / ymax;\n"
+         "          if (i) g.lineTo(x, y); else g.moveTo(x, y); }); g.stroke(); }\n"
+         "      if (s.name) g.fillText(s.name, L + W - 40 * (series.length - k), 18);\n"
+         "    });\n"
+         "  }\n"
+         "  for (var k in data) draw(k, data[k]);\n"
+         "})();\n"
          "</script>\n";
     std::time_t now = std::time(nullptr);
     char buf[80];
