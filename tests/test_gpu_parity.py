@@ -891,20 +891,45 @@ def test_align_long_queries_vs_oracle_and_edlib():
             assert int(r[f]) == (o[f] & 0xffffffff if f == "loc_hash" else o[f]), (f, len(p[0]), len(p[1]), p[2])
     if ref_lib.available():
         ref = ref_lib.edlib_batch(pairs)
-        hirschberg = 0
         for p, r, (d, alen, locs) in zip(pairs, out, ref):
-            assert int(r["edit_distance"]) == d and int(r["n_locations"]) == len(locs), (len(p[0]), len(p[1]), p[2])
-            # edlib switches from the traceback to Hirschberg's divide and conquer when the stored matrix of the
-            # located alignment would reach 1 MiB (E.cpp:1194-1215); that split picks other optimal paths in ties, so
-            # only there the alignment LENGTH may differ (library and oracle implement the traceback)
-            tl = locs[0][1] - locs[0][0] + 1 if locs else 0
-            big = (20 * ((len(p[0]) + 63) // 64)) * tl + 8 * tl >= 1 << 20
-            hirschberg += big
-            if not big:
-                assert int(r["align_len"]) == alen, (len(p[0]), len(p[1]), p[2])
+            assert int(r["edit_distance"]) == d and int(r["n_locations"]) == len(locs) and int(r["align_len"]) == alen, \
+                (len(p[0]), len(p[1]), p[2])
             if locs:
                 assert (int(r["first_start"]), int(r["first_end"])) == locs[0]
                 assert (int(r["last_start"]), int(r["last_end"])) == locs[-1]
+
+
+def test_align_hirschberg_sized_alignments_vs_oracle_and_edlib():
+    """edlib leaves the traceback for Hirschberg's divide and conquer when the matrix of the located alignment would
+    reach 1 MiB (E.cpp:1194-1215: adapters above ~1 250 bp with long, heavily mismatched hits); the split picks other
+    optimal paths in ties, so the alignment LENGTH depends on it.  Library and oracle reproduce the split rule."""
+    import ref_lib
+    rng = np.random.default_rng(2024)
+    a = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pairs = []
+    for i in range(150):
+        ql = int(rng.integers(1300, 2049))
+        alpha = a if i % 3 else a[:2]
+        q = alpha[rng.integers(0, len(alpha), ql)].tobytes()
+        if i % 5 == 4:
+            q = (q[:int(rng.integers(3, 40))] * 3000)[:ql]  # periodic query: masses of ties
+        m = synth.mutate(q, float(rng.random() * 0.35), rng)
+        t = (alpha[rng.integers(0, len(alpha), int(rng.integers(0, 200)))].tobytes() + m
+             + alpha[rng.integers(0, len(alpha), int(rng.integers(0, 200)))].tobytes())
+        pairs.append((q, t, [-1, ql, int(ql * 0.5)][i % 3]))
+    out = align_hw(pairs)
+    ref = ref_lib.edlib_batch(pairs) if ref_lib.available() else None
+    big = 0
+    for n, (p, r) in enumerate(zip(pairs, out)):
+        o, _ = oracle_lib.align_hw(*p)
+        for f in ("edit_distance", "n_locations", "align_len", "first_start", "first_end", "last_start", "last_end"):
+            assert int(r[f]) == o[f], (f, len(p[0]), len(p[1]), p[2])
+        tl = int(r["first_end"]) - int(r["first_start"]) + 1
+        big += (20 * ((len(p[0]) + 63) // 64) + 8) * tl >= 1 << 20
+        if ref is not None:
+            d, alen, locs = ref[n]
+            assert (o["edit_distance"], o["align_len"], o["n_locations"]) == (d, alen, len(locs)), (len(p[0]), len(p[1]), p[2])
+    assert big >= 30  # the split really was exercised
 
 
 def _long_adapter_batch(adapters, n=160, seed=5):

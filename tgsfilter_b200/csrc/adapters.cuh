@@ -311,7 +311,7 @@ k_mid_count(DevBatch B, AdapterCtx C, int a, int end_len, int n_adapters,
         const u64 s0 = shw_start<NW>(T, B.bases, mb, first, d);
         int ok = mlen_decision(T.qlen, (int)(first - s0 + 1), d, A.thr_mid);
         if (ok < 0) {
-            const int alen = nw_traceback_len<NW>(T, B.bases, s0, first, scratch + tid, scratch_stride);
+            const int alen = nw_alignment_len<NW>(T, B.bases, s0, first, d, scratch + tid, scratch_stride);
             ok = (alen - d >= A.thr_mid) ? 1 : 0;
         }
         mid_n[(u64)r * n_adapters + a] = ok ? count : 0u;
@@ -447,7 +447,7 @@ k_ends(DevBatch B, AdapterCtx C, int a0, int a1, int end_len, int n_adapters,
                 const u64 s0 = shw_start<NW>(T[x], B.bases, lo[x], first[x], d[x]);
                 int ok = mlen_decision(T[x].qlen, (int)(first[x] - s0 + 1), d[x], A[x].thr_end);
                 if (ok < 0) {
-                    const int alen = nw_traceback_len<NW>(T[x], B.bases, s0, first[x], scratch + tid, scratch_stride);
+                    const int alen = nw_alignment_len<NW>(T[x], B.bases, s0, first[x], d[x], scratch + tid, scratch_stride);
                     ok = (alen - d[x] >= A[x].thr_end) ? 1 : 0;
                 }
                 if (ok) {

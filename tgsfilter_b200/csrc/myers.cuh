@@ -207,13 +207,28 @@ static __device__ __forceinline__ int nw_cell(const u64 *Pv, const u64 *Mv, int 
     return v;
 }
 
-// alignmentLength of NW(query, target[s0..e0]) traced back Up > Left > Diagonal
+// Rows [off, off + len) of a table row (NW words) as the Peq words of that SUB-query (bits beyond len are 0).
+template <int NW>
+static __device__ __forceinline__ void eq_extract(const u64 *__restrict__ full, int off, int len, u64 *out) {
+    const int w0 = off >> 6, r = off & 63;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const u64 lo = (w0 + w < NW) ? full[w0 + w] : 0ull;
+        const u64 hi = (w0 + w + 1 < NW) ? full[w0 + w + 1] : 0ull;
+        u64 v = r ? ((lo >> r) | (hi << (64 - r))) : lo;
+        const int rem = len - 64 * w;
+        if (rem < 64) v = rem <= 0 ? 0ull : (v & ((1ull << rem) - 1ull));
+        out[w] = v;
+    }
+}
+
+// alignmentLength of NW(query[qoff .. qoff+q), target[s0..e0]) traced back Up > Left > Diagonal
 // (E.cpp:1023/1057/1088).  scratch: per-thread column store, element (col, k) at
 // scratch[(col * (2*NW+1) + k) * stride + tid]; must hold tl = e0 - s0 + 1 columns.
-template <int NW>
-static __device__ int nw_traceback_len(const AdapterTables &T, const uint8_t *__restrict__ bases,
-                                       u64 s0, u64 e0, u64 *scratch, u64 stride) {
-    const int q = T.qlen;
+// SUB: the query is a sub-range of the adapter (Hirschberg parts); its Peq words are cut out of the table rows.
+template <int NW, bool SUB>
+static __device__ int nw_traceback_len_impl(const AdapterTables &T, const uint8_t *__restrict__ bases, int qoff, int q,
+                                            u64 s0, u64 e0, u64 *scratch, u64 stride) {
     const int tl = (int)(e0 - s0 + 1);
     const int lastbit = q - 1;
     const int REC = 2 * NW + 1;
@@ -221,7 +236,13 @@ static __device__ int nw_traceback_len(const AdapterTables &T, const uint8_t *__
     myers_init_plain<NW>(s, q);
     for (int j = 0; j < tl; ++j) {
         const u64 *eq = T.fw + (u32)__ldg(bases + s0 + (u64)j) * NW;
-        myers_step<NW, 1, false>(s, eq, lastbit);
+        if (SUB) {
+            u64 eb[NW];
+            eq_extract<NW>(eq, qoff, q, eb);
+            myers_step<NW, 1, false>(s, eb, lastbit);
+        } else {
+            myers_step<NW, 1, false>(s, eq, lastbit);
+        }
         u64 *rec = scratch + (u64)j * REC * stride;
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
@@ -291,4 +312,79 @@ static __device__ int nw_traceback_len(const AdapterTables &T, const uint8_t *__
         }
     }
     return len;
+}
+
+template <int NW>
+static __device__ int nw_traceback_len(const AdapterTables &T, const uint8_t *__restrict__ bases,
+                                       u64 s0, u64 e0, u64 *scratch, u64 stride) {
+    return nw_traceback_len_impl<NW, false>(T, bases, 0, T.qlen, s0, e0, scratch, stride);
+}
+
+// alignmentLength the way obtainAlignment decides it (E.cpp:1164-1215): the traceback while the matrix edlib would
+// store stays below 1 MiB, otherwise Hirschberg's divide and conquer (E.cpp:1232-1390).  Only adapters above
+// ~1 250 bp can get there ((20 * ceil(q/64) + 8) * tl >= 2^20 with tl < 2q), so only the 32-word instantiation carries
+// the code.  The split: cut the target in the middle; the alignment passes between row i of the last left column
+// and row i + 1 of the first right column for the SMALLEST i (then the top, then the bottom boundary) whose scores
+// add up to the optimum; both parts are solved the same way (explicit stack instead of recursion).
+// `best` = the optimal distance of the whole problem (edlib passes it down as k).
+template <int NW>
+static __device__ int nw_alignment_len(const AdapterTables &T, const uint8_t *__restrict__ bases, u64 s0, u64 e0,
+                                       int best, u64 *scratch, u64 stride) {
+    if constexpr (NW < 32) {
+        return nw_traceback_len<NW>(T, bases, s0, e0, scratch, stride);
+    } else {
+        {   // the common case first: no split at all
+            const long long nb = (T.qlen + 63) / 64, tl = (long long)(e0 - s0 + 1);
+            if ((20 * nb + 8) * tl < (1ll << 20)) return nw_traceback_len<NW>(T, bases, s0, e0, scratch, stride);
+        }
+        struct Frame { int qoff, ql; u64 s, e1; int best; }; // target [s, e1)
+        Frame st[16];
+        int sp = 0, total = 0;
+        st[sp++] = Frame{0, T.qlen, s0, e0 + 1, best};
+        while (sp) {
+            const Frame f = st[--sp];
+            const int tl = (int)(f.e1 - f.s);
+            if (f.ql == 0 || tl == 0) { total += f.ql + tl; continue; } // E.cpp:1171-1178
+            const long long nb = (f.ql + 63) / 64;
+            if ((20 * nb + 8) * (long long)tl < (1ll << 20) || sp + 2 > 16) {
+                total += nw_traceback_len_impl<NW, true>(T, bases, f.qoff, f.ql, f.s, f.e1 - 1, scratch, stride);
+                continue;
+            }
+            const int lw = tl / 2, rw = tl - lw;
+            u64 eb[NW];
+            Myers<NW> a, b; // a: sub-query vs the left half; b: reversed sub-query vs the reversed right half
+            myers_init_plain<NW>(a, f.ql);
+            for (int j = 0; j < lw; ++j) {
+                eq_extract<NW>(T.fw + (u32)__ldg(bases + f.s + (u64)j) * NW, f.qoff, f.ql, eb);
+                myers_step<NW, 1, false>(a, eb, f.ql - 1);
+            }
+            myers_init_plain<NW>(b, f.ql);
+            const int roff = T.qlen - f.qoff - f.ql; // the same rows in the reversed-query table
+            for (int j = 0; j < rw; ++j) {
+                eq_extract<NW>(T.rv + (u32)__ldg(bases + (f.e1 - 1 - (u64)j)) * NW, roff, f.ql, eb);
+                myers_step<NW, 1, false>(b, eb, f.ql - 1);
+            }
+            // L[i] = lw + sum_{r <= i} da(r);  R[i + 1] = Rrev[ql - 2 - i] with Rrev[x] = rw + sum_{r <= x} db(r)
+            auto delta = [](const Myers<NW> &m, int r) {
+                return (int)((m.Pv[r >> 6] >> (r & 63)) & 1ull) - (int)((m.Mv[r >> 6] >> (r & 63)) & 1ull);
+            };
+            int idx = -2, ls = 0, rs = 0;
+            int Lc = lw, Rc = b.score; // before the loop: L[-1] = lw, Rrev[ql - 1] = b.score
+            for (int i = 0; i + 1 < f.ql; ++i) {
+                Lc += delta(a, i);
+                Rc -= delta(b, f.ql - 1 - i);
+                if (Lc + Rc == f.best) { idx = i; ls = Lc; rs = Rc; break; }
+            }
+            if (idx == -2 && lw + b.score == f.best) { idx = -1; ls = lw; rs = b.score; }
+            if (idx == -2 && a.score + rw == f.best) { idx = f.ql - 1; ls = a.score; rs = rw; }
+            if (idx == -2) { // cannot happen for a correct optimum: fall back to the traceback
+                total += nw_traceback_len_impl<NW, true>(T, bases, f.qoff, f.ql, f.s, f.e1 - 1, scratch, stride);
+                continue;
+            }
+            const int ul = idx + 1;
+            st[sp++] = Frame{f.qoff + ul, f.ql - ul, f.s + (u64)lw, f.e1, rs};
+            st[sp++] = Frame{f.qoff, ul, f.s, f.s + (u64)lw, ls};
+        }
+        return total;
+    }
 }

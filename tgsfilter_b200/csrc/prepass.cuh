@@ -49,7 +49,7 @@ k_lib_search(const uint8_t *__restrict__ rows, u32 n, u32 row_len, AdapterCtx C,
             myers_step<NW, 0, true>(s, T.hw + (u32)__ldg(rows + p) * NW, 0);
             if (s.score == d) {
                 const u64 s0 = shw_start<NW>(T, rows, lo, p, d);
-                const int alen = nw_traceback_len<NW>(T, rows, s0, p, scratch + tid, scratch_stride);
+                const int alen = nw_alignment_len<NW>(T, rows, s0, p, d, scratch + tid, scratch_stride);
                 acc += alen - d;
                 break;
             }
@@ -117,7 +117,7 @@ k_align_pairs(const uint8_t *__restrict__ targets, const u32 *__restrict__ t_off
                 if (s.score != d) continue;
                 const u64 s0 = shw_start<NW>(T, targets, lo, p, d);
                 if (nloc == 0)
-                    R.align_len = nw_traceback_len<NW>(T, targets, s0, p, scratch + tid, scratch_stride);
+                    R.align_len = nw_alignment_len<NW>(T, targets, s0, p, d, scratch + tid, scratch_stride);
                 add((int)(s0 - lo), (int)(p - lo));
             }
             R.n_locations = nloc;
