@@ -658,12 +658,18 @@ def main():
                 raise RuntimeError(f"tgsf_pack_bases: status {rc}, {ne} exceptions")
         pack_seconds[0] += time.perf_counter() - tq
 
+    pack_driver = ThreadPoolExecutor(1)  # packs sub-batch i + 1 while the main thread submits / collects sub-batch i
+
     def step_e2e_packed():
         nonlocal d2h_bytes
         d2h = 0
         inflight = 0
-        for b, s0, nr, o_t, nb, po in sub:
-            pack_sub(b, s0, nb, po)  # overlaps the H2D copy and the kernels of the previous sub-batch
+        fut = pack_driver.submit(pack_sub, sub[0][0], sub[0][1], sub[0][4], sub[0][5]) if sub else None
+        for i, (b, s0, nr, o_t, nb, po) in enumerate(sub):
+            fut.result()  # the packed bases of this sub-batch are in the pinned staging buffer
+            if i + 1 < len(sub):
+                nx = sub[i + 1]
+                fut = pack_driver.submit(pack_sub, nx[0], nx[1], nx[4], nx[5])
             if inflight == 2:
                 r, pcs = eng.collect()
                 d2h += r.nbytes + pcs.nbytes
