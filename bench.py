@@ -849,20 +849,24 @@ def main():
                "hbm_view": {"achieved_gbs": kmer_inserts, "frac_of_hbm": kmer_inserts / hbm_peak,
                             "work": "1 B per kept base (SURVEY.md §8d)"},
                "ms": kmer_ms, "share_of_step": share(kmer_ms)}
-    # measured DRAM traffic per launch (one ncu --set full capture of this same command, committed
-    # under profiles/); only valid for the workload it was captured on
+    # measured DRAM traffic per launch (one ncu --set full capture of this same command, committed under profiles/;
+    # the launches of the step's FIRST batch); only valid for the workload it was captured on
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tr = json.load(f)
-        if tr.get("config") == cfg and tr.get("reads_per_gpu") == local_reads and len(batches) == 1:
-            rl_mid["traffic"] = tr["k_mid_scan"]["dram_bytes"]
-            mid_all = lens - 2 * E
+        b0 = batches[0]
+        if tr.get("config") == cfg and tr.get("reads_per_launch") == b0.n_reads and tr.get("seed") == plan[0][2]:
+            lens0 = np.diff(b0.offsets)
+            mid0 = lens0 - 2 * E
             qmin = min(len(a) for a in params.adapters)
+            rl_mid["traffic"] = tr["k_mid_scan"]["dram_bytes"]
             # 1 B per middle-window column of the reads that pass -q/-Q; one pass serves both adapters
-            rl_mid["algorithmic_bytes"] = int(int(mid_all[mid_all >= qmin].sum()) * active_frac)
+            rl_mid["algorithmic_bytes"] = int(int(mid0[mid0 >= qmin].sum()) * active_frac)
             rl_raw["traffic"] = tr["k_scan_tiles_raw"]["dram_bytes"]
-            rl_raw["algorithmic_bytes"] = 2 * local_bases
+            rl_raw["algorithmic_bytes"] = 2 * b0.n_bases
             rl_clean["traffic"] = tr["k_scan_tiles_clean"]["dram_bytes"]
+            for r in (rl_mid, rl_raw, rl_clean):
+                r["traffic_note"] = "per launch of the step's first batch (%d reads), ncu --set full, %s" % (b0.n_reads, tr.get("source"))
     except Exception:
         pass
     by_stage = {"mid_scan": rl_mid, "raw_scan": rl_raw, "clean": rl_clean, "kmer": rl_kmer}
