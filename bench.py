@@ -451,6 +451,7 @@ def main():
                     help="weak mode: feed the dataset as at least this many batches (two are in flight at a time, so the "
                          "HBM-bound scans of one overlap the ALU-bound adapter scan of the other); default 2 for configs 2 and 3")
     ap.add_argument("--sample-reads", type=int, default=0, help="CPU reference: cap the reads per step (0 = whole dataset / time budget)")
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("TGSF_BENCH_SLOTS", "2")), help="batches in flight per context (1..4)")
     ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-fed measurement (profiling runs)")
@@ -555,7 +556,8 @@ def main():
         dist.broadcast_object_list(box, src=0)
         params = box[0]
     prepass_ms = (time.perf_counter() - t0) * 1e3
-    params.n_slots = 2
+    params.n_slots = max(1, min(4, args.slots))
+    n_slots = params.n_slots
     max_len = max(int(np.diff(b.offsets).max()) for b in batches)
     if max_len > 4_000_000:
         params.max_read_len = max_len
@@ -592,7 +594,7 @@ def main():
             for k in stage_acc:
                 stage_acc[k] += st[k]
         for b in batches:
-            if inflight == 2:
+            if inflight == n_slots:
                 retire()
                 inflight -= 1
             eng.submit_device(b.d_bases.data_ptr(), b.d_quals.data_ptr(), b.d_off.data_ptr(), b.n_reads, b.n_bases)
@@ -670,7 +672,7 @@ def main():
             if i + 1 < len(sub):
                 nx = sub[i + 1]
                 fut = pack_driver.submit(pack_sub, nx[0], nx[1], nx[4], nx[5])
-            if inflight == 2:
+            if inflight == n_slots:
                 r, pcs = eng.collect()
                 d2h += r.nbytes + pcs.nbytes
                 inflight -= 1
@@ -685,7 +687,7 @@ def main():
     def step_e2e_bytes():
         inflight = 0
         for b, s0, nr, o_t, nb, po in sub:
-            if inflight == 2:
+            if inflight == n_slots:
                 eng.collect()
                 inflight -= 1
             eng.submit_raw(b.h_bases.data_ptr() + s0, b.h_quals.data_ptr() + s0, o_t.data_ptr(), nr)

@@ -629,6 +629,8 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
         // no adapters: adapterMap still applies the fixed trims; no location arrays to read
         CU(cudaMemsetAsync(s.mid_n.p, 0, sizeof(u32), st));
     }
+    // the host copies an optimistic prefix of the piece array before the count is known (enqueue_d2h): define it
+    CU(cudaMemsetAsync(s.pieces.p, 0, (size_t)std::min<u32>(s.pieces_cap, n + 4096) * sizeof(tgsf_piece), st));
     k_regions<<<cdiv(n, REG_THREADS), REG_THREADS, 0, st>>>(
         s.B, P, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(), s.mid_n.as<u32>(),
         s.mid_off.as<u32>(), s.pool.as<Region>(), s.sortbuf.as<Region>(), s.pool_cap * 5, &H->sort_cursor,
