@@ -245,6 +245,7 @@ struct tgsf_ctx {
     bool kmer_force_tag32 = false;  // TGSF_KMER_TAG32=1: k <= 12 stays on k_kmer_smem alone (round-1 kernel; A/B, tests)
     int kmer16_ctas_per_sm = 2;
     int mid_ctas_per_sm = 0; // TGSF_MID_CTAS=n: cap on resident k_mid_scan CTAs per SM (0 = as many as fit)
+    bool max_carveout = false; // TGSF_CARVEOUT=1 (measured: no gain, see want_max_carveout)
     u32 kmer16_list_cap = KMER16_LIST_CAP; // TGSF_KMER16_LIST_CAP=n: smaller pending list (tests of the retry path)
     float last_kernel_ms = 0, last_total_ms = 0;
     float last_stage_ms[TGSF_N_STAGES] = {};
@@ -384,6 +385,18 @@ int for_nw(int nw, F f) {
     }
 }
 
+// Kernels that want different shared-memory carve-outs cannot be resident on one SM at the same time (the SM has to
+// drain before its L1 / shared split changes).  The K1 scan needs the maximum carve-out (197 KB of tiles and bins), so
+// every kernel that should be able to run NEXT to it (another batch's adapter scan, resolve and region kernels in the
+// other slot) would have to ask for the same split.  Measured on config[1] with two batches in flight (round 2):
+// 14.31 ms with the common carve-out vs 14.25 ms without, also when k_mid_scan leaves room (TGSF_MID_CTAS 3..5:
+// 15.4 / 14.5 / 14.4 ms) — the tails of one batch do not get under the other batch's scan this way either, so the
+// driver's choice stays the default; TGSF_CARVEOUT=1 turns the common split on (A/B).
+template <typename K>
+void want_max_carveout(const tgsf_ctx *c, K kern) {
+    if (c->max_carveout) cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
 int check_launch(const char *what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -515,6 +528,7 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                 TRY(for_nw(nw, [&](auto nwc) {
                     constexpr int NW = decltype(nwc)::value;
                     auto launch = [&](auto kern, size_t smem) {
+                        want_max_carveout(c, kern);
                         int occ = 0; // persistent grid: exactly the resident CTA count
                         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, MID_THREADS, smem) != cudaSuccess || occ < 1) occ = 4;
                         if (c->mid_ctas_per_sm > 0) occ = std::min(occ, c->mid_ctas_per_sm);
@@ -542,6 +556,7 @@ int launch_head(tgsf_ctx *c, Slot &s) {
             const int grid_a = Scratch::grid_for(res_grid, RES_THREADS, 2 * Ah.qlen + 2, Ah.nw);
             TRY(for_nw(Ah.nw, [&](auto nwc) {
                 constexpr int NW = decltype(nwc)::value;
+                want_max_carveout(c, k_mid_count<NW>);
                 k_mid_count<NW><<<grid_a, RES_THREADS, 0, st>>>(
                     s.B, AC, a, P.end_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(), s.chunks_cap,
                     s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(), s.chunk_first.as<u64>(),
@@ -563,6 +578,8 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                 const u64 stride_a = (u64)grid_a * RES_THREADS;
                 TRY(for_nw(nw, [&](auto nwc) {
                     constexpr int NW = decltype(nwc)::value;
+                    want_max_carveout(c, k_ends<NW, 1>);
+                    if constexpr (NW <= 2) want_max_carveout(c, k_ends<NW, 2>);
                     if constexpr (NW <= 2) {
                         if (a1 != a0)
                             k_ends<NW, 2><<<grid_a, RES_THREADS, 2 * 4 * 256 * NW * sizeof(u64), st>>>(
@@ -617,6 +634,7 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
             if (Ah.k_mid <= 0) continue;
             TRY(for_nw(Ah.nw, [&](auto nwc) {
                 constexpr int NW = decltype(nwc)::value;
+                want_max_carveout(c, k_mid_emit<NW>);
                 k_mid_emit<NW><<<res_grid, RES_THREADS, 0, st>>>(
                     s.B, AC, a, P.end_len, s.chunk_shift, P.extra_len, A, s.best_mid.as<u32>(), s.chunk_off.as<u32>(),
                     s.chunks.as<ChunkEntry>(), s.chunks_cap, s.chunk_min.as<uint8_t>(), s.chunk_hits.as<u32>(),
@@ -631,6 +649,7 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
     }
     // the host copies an optimistic prefix of the piece array before the count is known (enqueue_d2h): define it
     CU(cudaMemsetAsync(s.pieces.p, 0, (size_t)std::min<u32>(s.pieces_cap, n + 4096) * sizeof(tgsf_piece), st));
+    want_max_carveout(c, k_regions);
     k_regions<<<cdiv(n, REG_THREADS), REG_THREADS, 0, st>>>(
         s.B, P, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(), s.mid_n.as<u32>(),
         s.mid_off.as<u32>(), s.pool.as<Region>(), s.sortbuf.as<Region>(), s.pool_cap * 5, &H->sort_cursor,
@@ -848,6 +867,7 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
         c->kmer_force_bitmap = getenv("TGSF_KMER_BITMAP") != nullptr;
         c->kmer_force_tag32 = getenv("TGSF_KMER_TAG32") != nullptr;
         if (const char *e = getenv("TGSF_MID_CTAS")) c->mid_ctas_per_sm = atoi(e);
+        if (const char *e = getenv("TGSF_CARVEOUT")) c->max_carveout = atoi(e) != 0;
         if (const char *e = getenv("TGSF_KMER16_LIST_CAP")) c->kmer16_list_cap = (u32)std::min<long>(std::max<long>(atol(e), 32), (long)KMER16_LIST_CAP);
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
