@@ -1093,3 +1093,26 @@ def test_counter_block_grows_with_the_longest_read():
         a, b = getattr(g, name), getattr(o, name)
         m = min(len(a), len(b))
         assert np.array_equal(a[:m], b[:m]) and not a[m:].any() and not b[m:].any(), name
+
+
+@pytest.mark.parametrize("args", [["-F", "-R", "0.35"], ["-F", "-g", "60k", "-d", "4"], ["-x", "hifi", "-R", "0.5", "-5", "0", "-3", "0"]])
+def test_host_cli_downsampling_with_repeated_read_names(args):
+    """Input with repeated read names: DownSampleTask keys the lengths by NAME (the last record of a name wins,
+    T.cpp:2267) and keeps every record whose name was selected; with -F the fraction target counts EVERY record
+    (get_fastx_SeqLen adds all of them to totalSize, T.cpp:2262), in filter mode only the ranked names (T.cpp:2318-2322)."""
+    import ref_lib
+    if not ref_lib.available():
+        pytest.skip("oracle/_ref not present")
+    base = _distinct_length_batch(5, 180, seed=3)
+    seqs, quals, names = [], [], []
+    for i in range(base.n_reads):
+        b, q = base.read(i)
+        seqs.append(b.tobytes())
+        quals.append(q.tobytes())
+        names.append(base.name(i // 3 * 3) if i % 3 == 2 else base.name(i))  # every third record repeats an earlier name
+    fq = synth.pack_reads(seqs, quals, names).to_fastq()
+    r_rc, r_out, r_err, _ = ref_lib.run_cli(args + ["-t", "1"], fq)
+    h_rc, h_out, h_err = _run_host_cli(args, fq)
+    assert (h_rc, r_rc) == (0, 0), h_err
+    assert h_out == r_out and len(h_out) > 0
+    assert _info(h_err) == _info(r_err)
