@@ -66,7 +66,9 @@ typedef struct tgsf_params {
     int32_t n_adapters;     /* size of the global adapter set (both strands already inserted) */
     const uint8_t *const *adapter_seq; /* n_adapters byte strings (compared byte-wise like edlib) */
     const int32_t *adapter_len;
-    int32_t max_read_len;   /* capacity of the per-100 bp QC bins; 0 -> 4 Mi bases */
+    int32_t max_read_len;   /* INITIAL capacity of the per-100 bp QC bins (0 -> 4 Mi bases); tgsf_submit / tgsf_submit_packed
+                             * grow the counter block when a batch brings a longer read (ask tgsf_counter_layout_get again
+                             * before tgsf_counters); tgsf_submit_device cannot see the lengths: size it up front there */
     int32_t n_slots;        /* batches in flight (1..4); 0 -> 2 */
 } tgsf_params;
 
