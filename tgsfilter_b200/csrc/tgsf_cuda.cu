@@ -245,6 +245,7 @@ struct tgsf_ctx {
     bool kmer_force_tag32 = false;  // TGSF_KMER_TAG32=1: k <= 12 stays on k_kmer_smem alone (round-1 kernel; A/B, tests)
     int kmer16_ctas_per_sm = 2;
     int mid_ctas_per_sm = 0; // TGSF_MID_CTAS=n: cap on resident k_mid_scan CTAs per SM (0 = as many as fit)
+    int res_ctas_per_sm = 6; // grid of the resolve kernels (k_ends, k_mid_count, k_mid_emit) in CTAs per SM; TGSF_RES_CTAS
     bool max_carveout = false; // TGSF_CARVEOUT=1 (measured: no gain, see want_max_carveout)
     u32 kmer16_list_cap = KMER16_LIST_CAP; // TGSF_KMER16_LIST_CAP=n: smaller pending list (tests of the retry path)
     float last_kernel_ms = 0, last_total_ms = 0;
@@ -363,7 +364,7 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.h_res.ensure(((size_t)n + 1) * sizeof(tgsf_read_result)));
     TRY(s.h_pieces.ensure(((size_t)n + 4096) * sizeof(tgsf_piece)));
     TRY(s.h_header.ensure(sizeof(DevHeader)));
-    TRY(s.scratch.ensure(c->ads.host, c->sm_count * 4, RES_THREADS));
+    TRY(s.scratch.ensure(c->ads.host, c->sm_count * c->res_ctas_per_sm, RES_THREADS));
     return TGSF_OK;
 }
 
@@ -507,7 +508,7 @@ int launch_head(tgsf_ctx *c, Slot &s) {
         c->launches += 3;
         const AdapterCtx AC = c->ads.ctx();
         const u32 *n_chunks_ptr = s.chunk_off.as<u32>() + n;
-        const int res_grid = c->sm_count * 4;
+        const int res_grid = c->sm_count * c->res_ctas_per_sm;
         int mid_launch = 0;
         CU(cudaMemsetAsync(s.mid_work.p, 0, (size_t)A * sizeof(u32), st));
         // adapters with a live middle search, paired by word count: two per thread (long adapters: one)
@@ -627,7 +628,7 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
     }
     const bool filter = (P.flags & TGSF_FLAG_FILTER) != 0;
     const AdapterCtx AC = c->ads.ctx();
-    const int res_grid = c->sm_count * 4;
+    const int res_grid = c->sm_count * c->res_ctas_per_sm;
     if (filter && A > 0) {
         for (int a = 0; a < A; ++a) {
             const DevAdapter &Ah = c->ads.host[(size_t)a];
@@ -868,6 +869,7 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
         c->kmer_force_tag32 = getenv("TGSF_KMER_TAG32") != nullptr;
         if (const char *e = getenv("TGSF_MID_CTAS")) c->mid_ctas_per_sm = atoi(e);
         if (const char *e = getenv("TGSF_CARVEOUT")) c->max_carveout = atoi(e) != 0;
+        if (const char *e = getenv("TGSF_RES_CTAS")) c->res_ctas_per_sm = std::max(1, std::min(16, atoi(e)));
         if (const char *e = getenv("TGSF_KMER16_LIST_CAP")) c->kmer16_list_cap = (u32)std::min<long>(std::max<long>(atol(e), 32), (long)KMER16_LIST_CAP);
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
         cudaError_t e4 = cudaFuncSetAttribute(k_kmer<u64>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
