@@ -9,6 +9,11 @@
 // record starts at the next line beginning with '@' / '>', '\r' before '\n' is dropped, an empty or
 // length-mismatched quality line stops the input with the reference's message.
 #pragma once
+#ifdef TGSF_HAVE_HTSLIB
+// Optional: CRAM input through an htslib the build was pointed at (src/Makefile: HTS_DIR).  BAM and SAM never go
+// through it (own parser below); CRAM needs htslib's codecs and container logic, as in the reference (T.cpp:984-1040).
+#include "sam.h"
+#endif
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -68,6 +73,7 @@ private:
 class FastParser {
 public:
     FastParser(const std::string &path, bool fastq, bool sambam = false) : fastq_(fastq), sambam_(sambam) {
+        path_ = path;
         // plain files are read with read(2) straight into the parse buffer; gzip goes through zlib
         FILE *probe = fopen(path.c_str(), "rb");
         unsigned char magic[2] = {0, 0};
@@ -119,6 +125,11 @@ public:
         }
         if (f_) gzclose(f_);
         if (fd_ >= 0) close(fd_);
+#ifdef TGSF_HAVE_HTSLIB
+        if (cram_rec_) bam_destroy1(cram_rec_);
+        if (cram_hdr_) bam_hdr_destroy(cram_hdr_);
+        if (cram_) hts_close(cram_);
+#endif
     }
     bool ok() const { return f_ != nullptr || fd_ >= 0 || gz_ != nullptr || bgzf_ != nullptr || mm_ != nullptr || ss_ != nullptr; }
     static int inflate_threads() { // TGSF_INFLATE_THREADS, default min(8, cores - 2)
@@ -217,10 +228,21 @@ private:
         if (sb_state_ == 0) {
             if (!ensure(4)) return false;
             if (memcmp(buf_.data() + pos_, "CRAM", 4) == 0) {
-                std::cerr << "Error: CRAM input is not supported (convert with `samtools fastq` or to BAM)" << std::endl;
+#ifdef TGSF_HAVE_HTSLIB
+                cram_ = hts_open(path_.c_str(), "r");
+                if (!cram_) { std::cerr << "Error: Failed to open file: " << path_ << std::endl; return false; }
+                hts_set_opt(cram_, HTS_OPT_NTHREADS, inflate_threads());
+                hts_set_log_level(HTS_LOG_OFF);
+                cram_hdr_ = sam_hdr_read(cram_);
+                cram_rec_ = bam_init1();
+                if (!cram_hdr_ || !cram_rec_) { std::cerr << "Error: bad CRAM header: " << path_ << std::endl; return false; }
+                sb_state_ = 3;
+#else
+                std::cerr << "Error: CRAM input needs a build with htslib (make -C src HTS_DIR=<htslib prefix>); "
+                             "convert with `samtools fastq` or to BAM" << std::endl;
                 return false;
-            }
-            if (memcmp(buf_.data() + pos_, "BAM\1", 4) == 0) {
+#endif
+            } else if (memcmp(buf_.data() + pos_, "BAM\1", 4) == 0) {
                 if (!ensure(8)) return false;
                 const size_t l_text = rd32(pos_ + 4);
                 if (!ensure(12 + l_text)) return false;
@@ -243,6 +265,26 @@ private:
                 }
             }
         }
+#ifdef TGSF_HAVE_HTSLIB
+        if (sb_state_ == 3) { // CRAM record decoded by htslib, converted exactly like a BAM record (T.cpp:1003-1027)
+            if (sam_read1(cram_, cram_hdr_, cram_rec_) < 0) return false;
+            const size_t l_seq = (size_t)cram_rec_->core.l_qseq;
+            r.name = bam_get_qname(cram_rec_);
+            r.name_len = strlen(r.name);
+            sb_seq_.resize(l_seq);
+            sb_qual_.resize(l_seq);
+            const uint8_t *sq = bam_get_seq(cram_rec_), *ql = bam_get_qual(cram_rec_);
+            for (size_t i = 0; i < l_seq; ++i) {
+                sb_seq_[i] = kBase[bam_seqi(sq, i)];
+                sb_qual_[i] = (char)(ql[i] + 33);
+            }
+            r.seq = sb_seq_.data();
+            r.seq_len = l_seq;
+            r.qual = sb_qual_.data();
+            r.qual_len = l_seq;
+            return true;
+        }
+#endif
         if (sb_state_ == 1) { // BAM record: block_size, 32 fixed bytes, name, cigar, 4-bit bases, qualities, tags
             if (!ensure(4)) return false;
             const size_t bs = rd32(pos_);
@@ -310,7 +352,13 @@ private:
         r.qual_len = sb_qual_.size();
         return true;
     }
-    int sb_state_ = 0; // 0: container not looked at yet, 1: BAM records, 2: SAM lines
+    int sb_state_ = 0; // 0: container not looked at yet, 1: BAM records, 2: SAM lines, 3: CRAM through htslib
+    std::string path_;
+#ifdef TGSF_HAVE_HTSLIB
+    htsFile *cram_ = nullptr;
+    bam_hdr_t *cram_hdr_ = nullptr;
+    bam1_t *cram_rec_ = nullptr;
+#endif
     std::vector<char> sb_seq_, sb_qual_;
     uint8_t sam_code_[256];
 

@@ -1116,3 +1116,25 @@ def test_host_cli_downsampling_with_repeated_read_names(args):
     assert (h_rc, r_rc) == (0, 0), h_err
     assert h_out == r_out and len(h_out) > 0
     assert _info(h_err) == _info(r_err)
+
+
+def test_host_cli_cram_input():
+    """CRAM content (in a file named .bam, the only way it reaches the reference: GetFileType knows sam / bam only while
+    hts_open sniffs the content, T.cpp:839-857, 984-1040).  The CLI decodes it through htslib when the build was
+    pointed at one (src/Makefile HTS_DIR) and must write what it writes for the same reads as FASTQ, and what the
+    reference CLI writes for the same file.  Fixture: tests/golden/reads_cram.bam (tests/golden/make_cram.py)."""
+    import ref_lib
+    with open(golden_lib.HERE + "/reads_cram.bam", "rb") as f:
+        cram = f.read()
+    assert cram[:4] == b"CRAM"
+    fq = synth.make_config(2, 48, max_len=9000, with_names=False).to_fastq()
+    rc1, out1, err1 = _run_host_cli(["-x", "ont"], cram, in_name="in.bam")
+    if rc1 != 0 and "needs a build with htslib" in err1:
+        pytest.skip("src/tgsfilter was built without htslib")
+    rc0, out0, err0 = _run_host_cli(["-x", "ont"], fq)
+    assert rc0 == 0 and rc1 == 0, (err0, err1)
+    assert len(out0) > 10000 and out1 == out0
+    assert _info(err1) == _info(err0)
+    if ref_lib.available():
+        r_rc, r_out, r_err, _ = ref_lib.run_cli(["-x", "ont", "-t", "1"], cram, in_name="in.bam")
+        assert r_rc == 0 and r_out == out1 and _info(r_err) == _info(err1)
