@@ -207,6 +207,8 @@ struct DevHeader { // small block mirrored to the host with every batch
 
 struct Slot {
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;              // side stream: the end-window search runs next to the middle scan
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
     cudaEvent_t ev_stage[TGSF_N_STAGES + 1] = {};
     bool busy = false;
@@ -221,7 +223,7 @@ struct Slot {
     int chunk_shift = MID_CHUNK_SHIFT_MIN;
     DBuf best_mid, mid_n, mid_off, end_n, end_pos, pool, sortbuf, tmp, pieces, res, header;
     DBuf scan_tmp, kmer_bitmaps, kmer_long_list, mid_work, gz_blob, gz_spans;
-    Scratch scratch;
+    Scratch scratch, scratch2; // traceback stores: main stream (k_mid_count) / side stream (k_ends)
     u32 pool_cap = 0, pieces_cap = 0, chunks_cap = 0, tiles_cap = 0;
     // host results
     HBuf h_res, h_pieces, h_header;
@@ -246,6 +248,7 @@ struct tgsf_ctx {
     int kmer16_ctas_per_sm = 2;
     int mid_ctas_per_sm = 0; // TGSF_MID_CTAS=n: cap on resident k_mid_scan CTAs per SM (0 = as many as fit)
     int res_ctas_per_sm = 6; // grid of the resolve kernels (k_ends, k_mid_count, k_mid_emit) in CTAs per SM; TGSF_RES_CTAS
+    bool fork_ends = true; // TGSF_FORK_ENDS=0: k_ends on the batch's main stream after the middle scan (A/B)
     bool max_carveout = false; // TGSF_CARVEOUT=1 (measured: no gain, see want_max_carveout)
     u32 kmer16_list_cap = KMER16_LIST_CAP; // TGSF_KMER16_LIST_CAP=n: smaller pending list (tests of the retry path)
     float last_kernel_ms = 0, last_total_ms = 0;
@@ -283,6 +286,9 @@ int exclusive_scan(tgsf_ctx *c, cudaStream_t st, const u32 *in, u32 *out, u32 n,
 
 int slot_init(Slot &s) {
     CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s.stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&s.ev_join, cudaEventDisableTiming));
     CU(cudaEventCreate(&s.ev_start));
     CU(cudaEventCreate(&s.ev_k0));
     CU(cudaEventCreate(&s.ev_k1));
@@ -296,7 +302,7 @@ void slot_release(Slot &s) {
                     &s.seg_flag, &s.tile_cnt, &s.tile_off, &s.tiles, &s.read_active, &s.piece_cnt,
                     &s.piece_begin, &s.chunk_cnt, &s.chunk_off, &s.chunks, &s.chunk_min, &s.chunk_hits, &s.chunk_first, &s.chunk_perm, &s.chunk_hist,
                     &s.best_mid, &s.mid_n, &s.mid_off, &s.end_n, &s.end_pos, &s.pool, &s.sortbuf,
-                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.kmer_long_list, &s.mid_work, &s.gz_blob, &s.gz_spans, &s.scratch.buf};
+                    &s.tmp, &s.pieces, &s.res, &s.header, &s.scan_tmp, &s.kmer_bitmaps, &s.kmer_long_list, &s.mid_work, &s.gz_blob, &s.gz_spans, &s.scratch.buf, &s.scratch2.buf};
     for (DBuf *b : bufs) b->release();
     s.h_res.release();
     s.h_pieces.release();
@@ -307,6 +313,9 @@ void slot_release(Slot &s) {
     if (s.ev_end) cudaEventDestroy(s.ev_end);
     for (auto &e : s.ev_stage)
         if (e) cudaEventDestroy(e);
+    if (s.ev_fork) cudaEventDestroy(s.ev_fork);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
+    if (s.stream2) cudaStreamDestroy(s.stream2);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -365,6 +374,7 @@ int slot_reserve(tgsf_ctx *c, Slot &s, u32 n, u64 n_bases) {
     TRY(s.h_pieces.ensure(((size_t)n + 4096) * sizeof(tgsf_piece)));
     TRY(s.h_header.ensure(sizeof(DevHeader)));
     TRY(s.scratch.ensure(c->ads.host, c->sm_count * c->res_ctas_per_sm, RES_THREADS));
+    if (c->fork_ends) TRY(s.scratch2.ensure(c->ads.host, c->sm_count * c->res_ctas_per_sm, RES_THREADS));
     return TGSF_OK;
 }
 
@@ -490,6 +500,56 @@ int launch_head(tgsf_ctx *c, Slot &s) {
 
     const bool filter = (P.flags & TGSF_FLAG_FILTER) != 0;
     if (filter && A > 0) {
+        // End windows (k_ends): they only need read_active, so they are forked onto the slot's side stream and run
+        // NEXT TO the middle scan: k_ends is a latency-bound serial chain per read end, k_mid_scan saturates the ALU
+        // pipe with few warps, and together they fill the SM better than one after the other.  Adapters of one or two
+        // words go two per thread (paired by word count).
+        const AdapterCtx ACe = c->ads.ctx();
+        const int res_grid_e = c->sm_count * c->res_ctas_per_sm;
+        auto launch_ends = [&](cudaStream_t es, Scratch &sc) -> int {
+            const AdapterCtx &AC = ACe;
+            const int res_grid = res_grid_e;
+        for (int nw : {1, 2, 3, 4, 8, 16, 32}) {
+            std::vector<int> grp;
+            for (int a = 0; a < A; ++a)
+                if (c->ads.host[(size_t)a].nw == nw) grp.push_back(a);
+            const size_t step = nw <= 2 ? 2 : 1;
+            for (size_t i = 0; i < grp.size(); i += step) {
+                const int a0 = grp[i], a1 = (step == 2 && i + 1 < grp.size()) ? grp[i + 1] : grp[i];
+                const int qmax = std::max(c->ads.host[(size_t)a0].qlen, c->ads.host[(size_t)a1].qlen);
+                const int grid_a = Scratch::grid_for(res_grid, RES_THREADS, 2 * qmax + 2, nw);
+                const u64 stride_a = (u64)grid_a * RES_THREADS;
+                TRY(for_nw(nw, [&](auto nwc) {
+                    constexpr int NW = decltype(nwc)::value;
+                    want_max_carveout(c, k_ends<NW, 1>);
+                    if constexpr (NW <= 2) want_max_carveout(c, k_ends<NW, 2>);
+                    if constexpr (NW <= 2) {
+                        if (a1 != a0)
+                            k_ends<NW, 2><<<grid_a, RES_THREADS, 2 * 4 * 256 * NW * sizeof(u64), es>>>(
+                                s.B, AC, a0, a1, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
+                                sc.buf.as<u64>(), stride_a);
+                        else
+                            k_ends<NW, 1><<<grid_a, RES_THREADS, 4 * 256 * NW * sizeof(u64), es>>>(
+                                s.B, AC, a0, a0, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
+                                sc.buf.as<u64>(), stride_a);
+                    } else {
+                        k_ends<NW, 1><<<grid_a, RES_THREADS, NW <= 4 ? 4 * 256 * NW * sizeof(u64) : 0, es>>>(
+                            s.B, AC, a0, a0, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
+                            sc.buf.as<u64>(), stride_a);
+                    }
+                    c->launches++;
+                    return check_launch("k_ends");
+                }));
+            }
+        }
+            return TGSF_OK;
+        };
+        if (c->fork_ends) {
+            CU(cudaEventRecord(s.ev_fork, st));
+            CU(cudaStreamWaitEvent(s.stream2, s.ev_fork, 0));
+            TRY(launch_ends(s.stream2, s.scratch2));
+            CU(cudaEventRecord(s.ev_join, s.stream2));
+        }
         k_count_chunks<<<cdiv(n, 256), 256, 0, st>>>(s.B, s.read_active.as<int>(), P.end_len, s.chunk_shift, c->ads.min_q,
                                                      s.chunk_cnt.as<u32>(), s.best_mid.as<u32>(),
                                                      s.mid_n.as<u32>(), A);
@@ -566,40 +626,8 @@ int launch_head(tgsf_ctx *c, Slot &s) {
                 return check_launch("k_mid_count");
             }));
         }
-        // end windows: adapters of one or two words go two per thread (paired by word count)
-        for (int nw : {1, 2, 3, 4, 8, 16, 32}) {
-            std::vector<int> grp;
-            for (int a = 0; a < A; ++a)
-                if (c->ads.host[(size_t)a].nw == nw) grp.push_back(a);
-            const size_t step = nw <= 2 ? 2 : 1;
-            for (size_t i = 0; i < grp.size(); i += step) {
-                const int a0 = grp[i], a1 = (step == 2 && i + 1 < grp.size()) ? grp[i + 1] : grp[i];
-                const int qmax = std::max(c->ads.host[(size_t)a0].qlen, c->ads.host[(size_t)a1].qlen);
-                const int grid_a = Scratch::grid_for(res_grid, RES_THREADS, 2 * qmax + 2, nw);
-                const u64 stride_a = (u64)grid_a * RES_THREADS;
-                TRY(for_nw(nw, [&](auto nwc) {
-                    constexpr int NW = decltype(nwc)::value;
-                    want_max_carveout(c, k_ends<NW, 1>);
-                    if constexpr (NW <= 2) want_max_carveout(c, k_ends<NW, 2>);
-                    if constexpr (NW <= 2) {
-                        if (a1 != a0)
-                            k_ends<NW, 2><<<grid_a, RES_THREADS, 2 * 4 * 256 * NW * sizeof(u64), st>>>(
-                                s.B, AC, a0, a1, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
-                                s.scratch.buf.as<u64>(), stride_a);
-                        else
-                            k_ends<NW, 1><<<grid_a, RES_THREADS, 4 * 256 * NW * sizeof(u64), st>>>(
-                                s.B, AC, a0, a0, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
-                                s.scratch.buf.as<u64>(), stride_a);
-                    } else {
-                        k_ends<NW, 1><<<grid_a, RES_THREADS, NW <= 4 ? 4 * 256 * NW * sizeof(u64) : 0, st>>>(
-                            s.B, AC, a0, a0, P.end_len, A, s.read_active.as<int>(), s.end_n.as<int>(), s.end_pos.as<int>(),
-                            s.scratch.buf.as<u64>(), stride_a);
-                    }
-                    c->launches++;
-                    return check_launch("k_ends");
-                }));
-            }
-        }
+        if (c->fork_ends) CU(cudaStreamWaitEvent(st, s.ev_join, 0)); // the end-window results (side stream)
+        else TRY(launch_ends(st, s.scratch));
         TRY(exclusive_scan(c, st, s.mid_n.as<u32>(), s.mid_off.as<u32>(), n * (u32)A, s.scan_tmp.as<u32>(),
                            s.scan_tmp.cap / sizeof(u32)));
         k_check_pool<<<1, 1, 0, st>>>(s.mid_off.as<u32>() + (size_t)n * A, s.pool_cap, status);
@@ -869,6 +897,7 @@ int tgsf_create(int device, const tgsf_params *params, tgsf_ctx **out) {
         c->kmer_force_tag32 = getenv("TGSF_KMER_TAG32") != nullptr;
         if (const char *e = getenv("TGSF_MID_CTAS")) c->mid_ctas_per_sm = atoi(e);
         if (const char *e = getenv("TGSF_CARVEOUT")) c->max_carveout = atoi(e) != 0;
+        if (const char *e = getenv("TGSF_FORK_ENDS")) c->fork_ends = atoi(e) != 0;
         if (const char *e = getenv("TGSF_RES_CTAS")) c->res_ctas_per_sm = std::max(1, std::min(16, atoi(e)));
         if (const char *e = getenv("TGSF_KMER16_LIST_CAP")) c->kmer16_list_cap = (u32)std::min<long>(std::max<long>(atol(e), 32), (long)KMER16_LIST_CAP);
         cudaError_t e3 = cudaFuncSetAttribute(k_kmer<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, KMER_SMEM_BYTES);
