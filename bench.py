@@ -912,7 +912,7 @@ def main():
     wi = k4_prof.get("warp_instructions_per_insert")
     kmer_peak = 4 * 148 * sm_clock * 1e6 / wi / 1e9 if wi else None
     rl_kmer = {"kernel": "k_kmer_tag16 (K4, k <= 12: owner-byte dense round + position-tag list rounds in shared memory, "
-                         "2 CTAs/SM, producer warps; pieces > 65 kb: k_kmer_smem; k = 13: L2 bitmap; k > 13: hash)",
+                         "2 CTAs/SM, producer warps; k = 13..16: the same with u16 entries; pieces > 65 kb: k_kmer_smem / hash; k > 16: hash)",
                "bound": "issue", "achieved": kmer_inserts, "peak": kmer_peak, "unit": "Ginserts/s",
                "frac": kmer_inserts / kmer_peak if kmer_peak else None, "traffic": None,
                "work": "1 set insert per kept base",

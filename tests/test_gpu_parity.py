@@ -628,11 +628,18 @@ def test_kmer_repeat_length_on_every_kernel_path(k, monkeypatch):
     length is below the bound."""
     # long reads: one pass / two passes / four passes of k_kmer_tag16, just above its 16-bit position range, and
     # several staged tiles of k_kmer_smem
-    batch = _repeat_batch(100 + k, long_read=[450000, 19000, 33000, 64990, 65100] if k in (5, 11, 12) else 0)
+    batch = _repeat_batch(100 + k, long_read=[450000, 19000, 33000, 64990, 65100] if k in (5, 11, 12, 13, 16) else 0)
     params = FilterParams(min_len=50, min_q=0.0, kmer=k, min_repeat=200, qtype=33, adapters=[],
                           max_read_len=500000)
     r, p, _ = _compare(params, batch)
     assert (p["status"] != 0).any() and (p["status"] == 0).any()
+    if k in (13, 14, 16):  # owner-u16 rounds: the retry path, and the round-1 kernels (L2 bitmap / hash) on the same input
+        monkeypatch.setenv("TGSF_KMER16_LIST_CAP", "64")
+        _compare(params, batch)
+        monkeypatch.delenv("TGSF_KMER16_LIST_CAP")
+        monkeypatch.setenv("TGSF_KMER_L2", "1")
+        _compare(params, batch)
+        monkeypatch.delenv("TGSF_KMER_L2")
     if k in (8, 11, 12):  # the other kernels for the same k on the same input
         monkeypatch.setenv("TGSF_KMER16_LIST_CAP", "64")  # nearly every pass overflows the pending list: retry path
         _compare(params, batch)

@@ -27,7 +27,8 @@ static __device__ __forceinline__ u32 base_code(uint8_t b) { // T.cpp:1709-1724
 template <typename KEY>
 __global__ void __launch_bounds__(KMER_THREADS, 1)
 k_kmer(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pieces_ptr,
-       u64 *__restrict__ counters, const u32 *__restrict__ dev_status) {
+       u64 *__restrict__ counters, const u32 *__restrict__ dev_status,
+       const u32 *__restrict__ piece_list) { // piece_list != null: n_pieces_ptr counts its entries (the pieces k_kmer_tag16 left)
     if (*dev_status != DEV_STATUS_OK) return;
     extern __shared__ __align__(16) uint8_t kmem[];
     KEY *table = (KEY *)kmem;
@@ -38,7 +39,8 @@ k_kmer(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict__ n_pi
     const u64 mask = (k >= 32) ? ~0ull : ((1ull << (2 * k)) - 1ull);
     const u32 n_pieces = *n_pieces_ptr;
 
-    for (u32 pi = blockIdx.x; pi < n_pieces; pi += gridDim.x) {
+    for (u32 li = blockIdx.x; li < n_pieces; li += gridDim.x) {
+        const u32 pi = piece_list ? piece_list[li] : li;
         tgsf_piece pc = pieces[pi];
         if (pc.status != TGSF_PIECE_EMIT) continue;
         const int L = pc.len;

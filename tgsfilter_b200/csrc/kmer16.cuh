@@ -1,13 +1,14 @@
-// K4, k <= 12, pieces of up to KMER16_MAX_KMERS k-mers: distinct k-mer count without shared-memory
+// K4, k <= 16, pieces of up to KMER16_MAX_KMERS k-mers: distinct k-mer count without shared-memory
 // atomics on the k-mer path.  Replaces GetKmerCount (T.cpp:1703-1753) for the common case (the default
-// k = 11 on HiFi / CLR / ordinary ONT pieces); longer pieces are handed to k_kmer_smem through a device
-// list.  Two CTAs per SM; inside a CTA two PRODUCER warps stage the next two pieces (global loads, ASCII
+// k = 11 on HiFi / CLR / ordinary ONT pieces); longer pieces are handed to k_kmer_smem (k <= 12) or k_kmer (hash)
+// through a device list.  Two CTAs per SM; inside a CTA two PRODUCER warps stage the next two pieces (global loads, ASCII
 // -> 2-bit codes, one tile buffer each) while 14 CONSUMER warps count the current one, so neither the
 // global-load latency nor the piece metadata chain is ever on the consumers' path (named barriers:
 // consumers among themselves, full / empty per tile buffer).
 //
 // Counting a staged piece (k16_count):
-//   * dense round, "owner bytes": the table is 65 536 BYTE slots.  slot = top 16 bits of the key, and
+//   * dense round, "owner bytes": the table is 65 536 BYTE slots (k = 13 .. 16: 32 768 u16 slots, the same scheme with
+//     15 remainder bits per entry).  slot = top 16 bits of the key, and
 //     every k-mer stores (low key bits | 0x80) there — no position, no atomics, last writer wins.  After
 //     one barrier a k-mer that reads back its own byte belongs to the key that owns the slot; all
 //     instances of a key share slot and verdict, so the keys resolved by the round are exactly the
@@ -143,17 +144,22 @@ static __device__ __forceinline__ void k16_append(u32 m, u32 pw, uint16_t *list,
 // One attempt at a staged piece with 2^pass_bits key classes (consumer threads only).  Returns false (in
 // every thread) if a pass produced more pending k-mers than the list holds; the caller retries with more
 // passes.  KT: compile-time k (0: use krt).
-template <int KT>
+// ENT: owner entry: uint8_t (k <= 12: 65 536 slots, 7 remainder bits) or uint16_t (k = 13 .. 16: 32 768 slots, 15 bits).
+template <int KT, typename ENT>
 static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *list_a, uint16_t *list_b, u32 *s_cnt,
                                  u32 shift, u32 p_end, int krt, u32 pass_bits, u32 list_cap, u32 &mine) {
     const int k = KT ? KT : krt;
     uint16_t *table = (uint16_t *)table8;
+    ENT *own = (ENT *)table8;
+    constexpr u32 SB = sizeof(ENT) == 1 ? 16u : 15u;             // slot bits
+    constexpr u32 FLAG = sizeof(ENT) == 1 ? 0x80u : 0x8000u;     // set in every stored entry: 0 = empty
+    constexpr u32 EMASK = sizeof(ENT) == 1 ? 0xFFu : 0xFFFFu;
     const u32 sh = 32u - 2u * (u32)k;            // x >> sh = key
-    const u32 slot_sh = sh > 16u ? sh : 16u;     // slot = top 16 bits of the key (the whole key when 2k <= 16)
+    const u32 slot_sh = sh > 32u - SB ? sh : 32u - SB; // slot = top SB bits of the key (the whole key when 2k <= SB)
     const u32 n_scan = (p_end + 15u) >> 4;       // words holding the start of at least one k-mer
     const u32 lane = threadIdx.x & 31u;
     const u32 n_pass = 1u << pass_bits;
-    const u32 cls_sh = 16u - pass_bits;          // class = top pass_bits bits of the remainder x[15 : sh]
+    const u32 cls_sh = 32u - SB - pass_bits;     // class = top pass_bits bits of the remainder x[31 - SB : sh]
     mine = 0;
     for (u32 pass = 0; pass < n_pass; ++pass) {
         k16_sync_consumers(); // previous pass / piece is done with the table, the lists and s_cnt
@@ -167,7 +173,7 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
 #pragma unroll
                 for (u32 j = 0; j < 16; ++j) {
                     const u32 x = __funnelshift_l(w1, w0, 2 * j);
-                    table8[x >> slot_sh] = (uint8_t)((x >> sh) | 0x80u);
+                    own[x >> slot_sh] = (ENT)((x >> sh) | FLAG);
                 }
             } else {
                 u32 m = 0xFFFFu;
@@ -177,7 +183,7 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
                 for (u32 j = 0; j < 16; ++j) {
                     const u32 x = __funnelshift_l(w1, w0, 2 * j);
                     if (((m >> j) & 1u) && (pass_bits == 0 || ((x >> cls_sh) & (n_pass - 1u)) == pass))
-                        table8[x >> slot_sh] = (uint8_t)((x >> sh) | 0x80u);
+                        own[x >> slot_sh] = (ENT)((x >> sh) | FLAG);
                 }
             }
         }
@@ -192,8 +198,8 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
 #pragma unroll
                     for (u32 j = 0; j < 16; ++j) {
                         const u32 x = __funnelshift_l(w1, w0, 2 * j);
-                        const u32 v = table8[x >> slot_sh];
-                        pend |= (v != (((x >> sh) | 0x80u) & 0xFFu)) ? (1u << j) : 0u;
+                        const u32 v = own[x >> slot_sh];
+                        pend |= (v != (((x >> sh) | FLAG) & EMASK)) ? (1u << j) : 0u;
                     }
                 } else {
                     u32 m = 0xFFFFu;
@@ -203,8 +209,8 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
                     for (u32 j = 0; j < 16; ++j) {
                         const u32 x = __funnelshift_l(w1, w0, 2 * j);
                         if (((m >> j) & 1u) && (pass_bits == 0 || ((x >> cls_sh) & (n_pass - 1u)) == pass)) {
-                            const u32 v = table8[x >> slot_sh];
-                            pend |= (v != (((x >> sh) | 0x80u) & 0xFFu)) ? (1u << j) : 0u;
+                            const u32 v = own[x >> slot_sh];
+                            pend |= (v != (((x >> sh) | FLAG) & EMASK)) ? (1u << j) : 0u;
                         }
                     }
                 }
@@ -214,7 +220,8 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
         // ---- the keys resolved by this round = the non-empty byte slots (every stored byte has bit 7 set) ----
         for (u32 i = threadIdx.x; i < KMER16_TABLE_BYTES / 16u; i += KMER16_CONSUMERS) {
             const uint4 q = ((const uint4 *)table8)[i];
-            mine += __popc(((q.x & 0x80808080u) >> 3) | ((q.y & 0x80808080u) >> 2) | ((q.z & 0x80808080u) >> 1) | (q.w & 0x80808080u));
+            constexpr u32 FM = sizeof(ENT) == 1 ? 0x80808080u : 0x80008000u; // the flag bit of every entry of a word
+            mine += __popc(((q.x & FM) >> 3) | ((q.y & FM) >> 2) | ((q.z & FM) >> 1) | (q.w & FM));
         }
         k16_sync_consumers();
         u32 n_list = s_cnt[0];
@@ -256,11 +263,14 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
             if (threadIdx.x == 0) s_cnt[ci] = 0; // next round's counter; nobody reads it before the next barrier
             uint16_t *t = cur; cur = nxt; nxt = t;
         }
-        if (n_list && threadIdx.x < 32u) { // the last few keys: one warp, one MATCH
+        if (n_list && threadIdx.x < 32u) { // the last few keys: one warp, one MATCH among the lanes that hold one
             const bool have = lane < n_list;
-            const u32 key = have ? (k16_kmer_at(tile, cur[lane]) >> sh) : (0xFFFFFFFFu - lane); // fillers are all distinct
-            const u32 same = __match_any_sync(0xffffffffu, key);
-            if (have && (u32)(__ffs((int)same) - 1) == lane) ++mine;
+            const u32 vmask = __ballot_sync(0xffffffffu, have);
+            if (have) {
+                const u32 key = k16_kmer_at(tile, cur[lane]) >> sh;
+                const u32 same = __match_any_sync(vmask, key);
+                if ((u32)(__ffs((int)same) - 1) == lane) ++mine;
+            }
         }
     }
     return true;
@@ -353,15 +363,23 @@ k_kmer_tag16(DevBatch B, DevParams P, tgsf_piece *pieces, const u32 *__restrict_
         }
         const u32 *tile = tiles + b * (KMER16_TILE_WORDS + 2u);
         if (threadIdx.x == 0) s_distinct = 0; // ordered before its use by the barriers inside k16_count
-        // classes split the key REMAINDER (2k - 16 bits; none for k <= 8, where slot = key and nothing can collide)
-        const u32 rem_bits = 2 * k > 16 ? (u32)(2 * k - 16) : 0u;
-        u32 pass_bits = rem_bits > 7u ? rem_bits - 7u : 0u; // an owner byte holds 7 remainder bits: k = 12 needs two classes
-        while (pass_bits < rem_bits && ((u32)M.total >> pass_bits) > KMER16_ONE_PASS) ++pass_bits;
+        // classes split the key REMAINDER (the 2k - 16 / 2k - 15 bits that are not in the slot; none for small k, where
+        // slot = key and nothing can collide).  An owner byte holds 7 remainder bits (k = 12 needs two classes), an
+        // owner u16 15 (k = 16: four); the u16 table has half the slots, so its passes start at half the piece size.
+        const bool wide = k > 12;
+        const u32 sb = wide ? 15u : 16u;
+        const u32 rem_bits = 2u * (u32)k > sb ? 2u * (u32)k - sb : 0u;
+        const u32 ent_bits = wide ? 15u : 7u;
+        const u32 one_pass = wide ? KMER16_ONE_PASS / 2u : KMER16_ONE_PASS;
+        u32 pass_bits = rem_bits > ent_bits ? rem_bits - ent_bits : 0u;
+        while (pass_bits < rem_bits && ((u32)M.total >> pass_bits) > one_pass) ++pass_bits;
         u32 mine = 0;
         if (k == 11) {
-            while (!k16_count<11>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
+            while (!k16_count<11, uint8_t>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
+        } else if (!wide) {
+            while (!k16_count<0, uint8_t>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
         } else {
-            while (!k16_count<0>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
+            while (!k16_count<0, uint16_t>(tile, table, list_a, list_b, s_cnt, M.shift, M.shift + (u32)M.total, k, pass_bits, list_cap, mine)) ++pass_bits;
         }
         mine = warp_sum_u32(mine);
         if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(&s_distinct, mine);

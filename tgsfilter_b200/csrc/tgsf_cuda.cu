@@ -695,15 +695,23 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
     c->launches++;
     CU(cudaEventRecord(s.ev_stage[5], st));
     if (!(P.flags & TGSF_FLAG_ONLY_QC)) {
-        if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2 && !c->kmer_force_bitmap && !c->kmer_force_tag32) {
-            // 16-bit position tags, two CTAs per SM; pieces too long for 16-bit positions go to k_kmer_smem
+        if (P.min_repeat > 0 && P.kmer <= 16 && !c->kmer_force_l2 && !c->kmer_force_bitmap && !c->kmer_force_tag32) {
+            // owner-entry rounds, two CTAs per SM; pieces too long for 16-bit positions go to k_kmer_smem (k <= 12) or
+            // to the hash kernel (k = 13 .. 16) through the long list
             TRY(s.kmer_long_list.ensure((size_t)s.pieces_cap * sizeof(u32)));
             k_kmer_tag16<<<c->sm_count * c->kmer16_ctas_per_sm, KMER16_THREADS, KMER16_SMEM_BYTES, st>>>(
                 s.B, P, s.pieces.as<tgsf_piece>(), &H->tmp_cursor, C, &H->status, &H->kmer_work,
                 s.kmer_long_list.as<u32>(), &H->kmer_long, c->kmer16_list_cap);
-            k_kmer_smem<<<c->sm_count, KMER_SB_THREADS, KMER_SB_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
-                                                                                 &H->kmer_long, C, &H->status, 0,
-                                                                                 s.kmer_long_list.as<u32>());
+            if (P.kmer <= 12)
+                k_kmer_smem<<<c->sm_count, KMER_SB_THREADS, KMER_SB_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
+                                                                                     &H->kmer_long, C, &H->status, 0,
+                                                                                     s.kmer_long_list.as<u32>());
+            else if (P.kmer <= 15)
+                k_kmer<u32><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(), &H->kmer_long, C,
+                                                                            &H->status, s.kmer_long_list.as<u32>());
+            else
+                k_kmer<u64><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(), &H->kmer_long, C,
+                                                                            &H->status, s.kmer_long_list.as<u32>());
             c->launches += 2;
         } else if (P.min_repeat > 0 && P.kmer <= 12 && !c->kmer_force_l2) {
             // round-1 path: 32-bit tag rounds / shared-memory bitmap in key-range passes, one CTA per SM
@@ -726,10 +734,10 @@ int launch_tail(tgsf_ctx *c, Slot &s) {
         } else if (P.min_repeat > 0) {
             if (P.kmer <= 15)
                 k_kmer<u32><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
-                                                                            &H->tmp_cursor, C, &H->status);
+                                                                            &H->tmp_cursor, C, &H->status, nullptr);
             else
                 k_kmer<u64><<<c->sm_count, KMER_THREADS, KMER_SMEM_BYTES, st>>>(s.B, P, s.pieces.as<tgsf_piece>(),
-                                                                            &H->tmp_cursor, C, &H->status);
+                                                                            &H->tmp_cursor, C, &H->status, nullptr);
             c->launches++;
         }
         CU(cudaEventRecord(s.ev_stage[6], st));
