@@ -175,6 +175,12 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
                     const u32 x = __funnelshift_l(w1, w0, 2 * j);
                     own[x >> slot_sh] = (ENT)((x >> sh) | FLAG);
                 }
+            } else if (pw >= shift && pw + 16u <= p_end) { // interior word of a multi-pass piece: unrolled, class-predicated
+#pragma unroll
+                for (u32 j = 0; j < 16; ++j) {
+                    const u32 x = __funnelshift_l(w1, w0, 2 * j);
+                    if (((x >> cls_sh) & (n_pass - 1u)) == pass) own[x >> slot_sh] = (ENT)((x >> sh) | FLAG);
+                }
             } else {
                 u32 m = 0xFFFFu;
                 if (pw < shift) m &= 0xFFFFu << (shift - pw);
@@ -200,6 +206,13 @@ static __device__ bool k16_count(const u32 *tile, uint8_t *table8, uint16_t *lis
                         const u32 x = __funnelshift_l(w1, w0, 2 * j);
                         const u32 v = own[x >> slot_sh];
                         pend |= (v != (((x >> sh) | FLAG) & EMASK)) ? (1u << j) : 0u;
+                    }
+                } else if (pw >= shift && pw + 16u <= p_end) { // interior word of a multi-pass piece
+#pragma unroll
+                    for (u32 j = 0; j < 16; ++j) {
+                        const u32 x = __funnelshift_l(w1, w0, 2 * j);
+                        const u32 v = own[x >> slot_sh];
+                        pend |= (((x >> cls_sh) & (n_pass - 1u)) == pass && v != (((x >> sh) | FLAG) & EMASK)) ? (1u << j) : 0u;
                     }
                 } else {
                     u32 m = 0xFFFFu;
